@@ -1,0 +1,28 @@
+"""fateavatar_b200 -- sm_100a 3D-Gaussian-splatting operators behind FateAvatar's rasterizer API.
+
+The package holds only the hot path: the CUDA kernels + C ABI (csrc/, lib/),
+and the Python mirror of the reference operator interface (rasterizer.py, knn.py, pose.py, render.py).
+
+    import fateavatar_b200; fateavatar_b200.install()
+    # from here on `import diff_gaussian_rasterization` / `from simple_knn._C import distCUDA2`
+    # resolve to the B200 implementation, so the reference's volume_rendering/*.py run unchanged.
+"""
+import os
+import sys
+
+__version__ = "0.1.0"
+
+_DROPIN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dropin")
+
+
+def install():
+    """Make the drop-in operator modules importable under the reference's module names."""
+    if _DROPIN not in sys.path:
+        sys.path.insert(0, _DROPIN)
+    for name in ("diff_gaussian_rasterization", "simple_knn", "simple_knn._C"):
+        mod = sys.modules.get(name)
+        if mod is not None and not getattr(mod, "__file__", "").startswith(_DROPIN):
+            del sys.modules[name]
+    import diff_gaussian_rasterization  # noqa: F401
+    import simple_knn._C  # noqa: F401
+    return _DROPIN

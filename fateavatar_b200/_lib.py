@@ -1,0 +1,92 @@
+"""ctypes binding of libfatesplat.so -- the only native code the product loads.
+
+There is NO fallback: if the shared object is missing or cannot be loaded, importing a drop-in operator
+raises.  The oracle under oracle/ is never consulted from here.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfatesplat.so")
+
+FS_OK = 0
+
+
+class FsFrameInfo(C.Structure):
+    _fields_ = [
+        ("num_rendered", C.c_uint32),
+        ("overflow", C.c_uint32),
+        ("num_visible", C.c_uint32),
+        ("max_tile_instances", C.c_uint32),
+        ("reserved", C.c_uint32 * 4),
+    ]
+
+
+_LAYOUT_FIELDS = [
+    "total_bytes", "info", "depths", "cov3D", "splat", "clamped", "rect", "tiles_touched", "tile_count",
+    "tile_cursor", "ranges", "big_tiles", "inst_keys", "inst_keys_alt", "point_list", "inst_splat", "final_T",
+    "n_contrib", "grad_acc", "instance_capacity",
+]
+
+
+class FsWorkspaceLayout(C.Structure):
+    _fields_ = [(n, C.c_size_t) for n in _LAYOUT_FIELDS]
+
+
+# every symbol include/fatesplat.h declares
+EXPORTS = [
+    "fs_workspace_bytes", "fs_get_workspace_layout", "fs_forward", "fs_backward", "fs_mark_visible",
+    "fs_knn_workspace_bytes", "fs_knn_mean_dist2", "fs_last_launch_count", "fs_last_error", "fs_version",
+]
+
+_lib = None
+
+
+class FateSplatError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (once) and type the library.  Raises FateSplatError when it is absent: no CPU path exists."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FateSplatError(
+            f"{LIB_PATH} not found: build it with `python -m fateavatar_b200.build` (needs nvcc, sm_100a). "
+            "fateavatar_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    vp, f, i, sz = C.c_void_p, C.c_float, C.c_int, C.c_size_t
+    lib.fs_workspace_bytes.restype = sz
+    lib.fs_workspace_bytes.argtypes = [i, i, i, sz]
+    lib.fs_get_workspace_layout.restype = i
+    lib.fs_get_workspace_layout.argtypes = [i, i, i, sz, C.POINTER(FsWorkspaceLayout)]
+    lib.fs_forward.restype = i
+    lib.fs_forward.argtypes = [i, i, i, vp, i, i, vp, vp, vp, vp, vp, f, vp, vp, vp, vp, vp, f, f, i, vp, vp, vp, sz,
+                               sz, vp, vp]
+    lib.fs_backward.restype = i
+    lib.fs_backward.argtypes = [i, i, i, vp, i, i, vp, vp, vp, vp, f, vp, vp, vp, vp, vp, f, f, vp, vp, sz, sz, vp,
+                                vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.fs_mark_visible.restype = i
+    lib.fs_mark_visible.argtypes = [i, vp, vp, vp, vp, vp]
+    lib.fs_knn_workspace_bytes.restype = sz
+    lib.fs_knn_workspace_bytes.argtypes = [i]
+    lib.fs_knn_mean_dist2.restype = i
+    lib.fs_knn_mean_dist2.argtypes = [i, vp, vp, vp, sz, vp]
+    lib.fs_last_launch_count.restype = i
+    lib.fs_last_error.restype = C.c_char_p
+    lib.fs_version.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != FS_OK:
+        raise FateSplatError(f"{what} failed ({rc}): {load().fs_last_error().decode()}")
+
+
+def workspace_layout(P, W, H, capacity):
+    L = FsWorkspaceLayout()
+    check(load().fs_get_workspace_layout(int(P), int(W), int(H), int(capacity), C.byref(L)), "fs_get_workspace_layout")
+    return L

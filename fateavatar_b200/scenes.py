@@ -1,0 +1,155 @@
+"""Deterministic synthetic workloads for tests and bench.py (BASELINE.json configs 1, 2, 5).
+
+Everything here is *input generation*: numpy float64 math cast to float32.  Camera matrices follow the
+reference's conventions (tools/gs_utils/graphics_utils.py:38-84, volume_rendering/camera_3dgs.py:53-72):
+`viewmatrix` = world-to-view transposed, `projmatrix` = viewmatrix @ projection^T, points are row vectors.
+"""
+import math
+
+import numpy as np
+
+SH_C0 = 0.28209479177387814
+
+
+def make_camera(W, H, fovx, fovy, R=None, T=None, znear=0.01, zfar=100.0):
+    """R: camera-to-world rotation (3x3), T: world-to-camera translation (3,), as `cam_pose` holds them
+    (SURVEY Appendix A).  Returns the tensors GaussianRasterizationSettings needs."""
+    R = np.diag([1.0, -1.0, -1.0]) if R is None else np.asarray(R, np.float64)
+    T = np.array([0.0, 0.0, 2.5]) if T is None else np.asarray(T, np.float64)
+    Rt = np.zeros((4, 4))
+    Rt[:3, :3] = R.T
+    Rt[:3, 3] = T
+    Rt[3, 3] = 1.0
+    view_t = Rt.T  # world_view_transform
+    ty, tx = math.tan(fovy / 2), math.tan(fovx / 2)
+    top, right = ty * znear, tx * znear
+    Pm = np.zeros((4, 4))
+    Pm[0, 0] = 2.0 * znear / (2 * right)
+    Pm[1, 1] = 2.0 * znear / (2 * top)
+    Pm[3, 2] = 1.0
+    Pm[2, 2] = zfar / (zfar - znear)
+    Pm[2, 3] = -(zfar * znear) / (zfar - znear)
+    full = view_t @ Pm.T
+    campos = np.linalg.inv(view_t)[3, :3]
+    return dict(W=int(W), H=int(H), fovx=float(fovx), fovy=float(fovy), tanfovx=math.tan(fovx * 0.5),
+                tanfovy=math.tan(fovy * 0.5), viewmatrix=view_t.astype(np.float32),
+                projmatrix=full.astype(np.float32), campos=campos.astype(np.float32))
+
+
+def orbit_camera(W, H, fov, k, n, radius=2.5):
+    """k-th of n views on a horizontal circle looking at the origin (the 360 degree sweep of config 5; same
+    parametrisation as LookAtPoseSampler.sample(pi/2 + 2 pi k/n, pi/2, 0, radius), camera_eg3d.py:36-54)."""
+    theta = math.pi / 2 + 2 * math.pi * k / n
+    origin = np.array([radius * math.cos(math.pi - theta), 0.0, radius * math.sin(math.pi - theta)])
+    fwd = -origin / np.linalg.norm(origin)
+    up = np.array([0.0, 1.0, 0.0])
+    right = np.cross(up, fwd)
+    right /= np.linalg.norm(right)
+    up2 = np.cross(fwd, right)
+    c2w_R = np.stack([right, -up2, fwd], axis=1)  # camera x right, y down, z forward
+    w2c_R = c2w_R.T
+    T = -w2c_R @ origin
+    return make_camera(W, H, fov, fov, R=c2w_R, T=T)
+
+
+def _quat(rng, n):
+    q = rng.standard_normal((n, 4))
+    return q / np.linalg.norm(q, axis=1, keepdims=True)
+
+
+def _sigmoid(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def config1_scene(seed=0, P=10000, W=256, H=256):
+    """BASELINE config 1: 10k random Gaussians, one static 256x256 camera, SH degree 0, white background."""
+    rng = np.random.default_rng(seed)
+    s = dict(
+        means3D=rng.uniform(-0.5, 0.5, (P, 3)),
+        scales=np.exp(rng.normal(math.log(0.01), 0.3, (P, 3))),
+        rotations=_quat(rng, P),
+        opacities=_sigmoid(rng.standard_normal((P, 1))),
+        shs=((rng.uniform(0, 1, (P, 1, 3)) - 0.5) / SH_C0),
+        sh_degree=0,
+        bg=np.ones(3),
+        camera=make_camera(W, H, 0.35, 0.35, T=[0, 0, 2.5]),
+        name=f"config1: {P} random Gaussians, {W}x{H}, SH0",
+    )
+    return _f32(s)
+
+
+def head_points(rng, P):
+    """Points on a head-sized ellipsoid shell (extents ~0.21 x 0.31 x 0.22 like the FLAME template)."""
+    d = rng.standard_normal((P, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    semi = np.array([0.105, 0.155, 0.11])
+    return d * semi * (1.0 + 0.01 * rng.standard_normal((P, 1)))
+
+
+def head_scene(seed=0, P=100000, W=512, H=512, sh_degree=0, scale_mult=1.0):
+    """BASELINE config 2 geometry: ~100k splats on a head-sized surface filling ~70 % of a 512x512 frame
+    (camera distance 1.25, fov 0.35 rad).  Scale = mean nearest-neighbour spacing (FateAvatar's init rule,
+    model/fateavatar.py:596-608) with log-normal anisotropy; opacity = sigmoid(N(0,1))."""
+    rng = np.random.default_rng(seed)
+    xyz = head_points(rng, P)
+    area = 4 * math.pi * (((0.105 * 0.155) ** 1.6075 + (0.105 * 0.11) ** 1.6075 + (0.155 * 0.11) ** 1.6075) / 3) ** (
+        1 / 1.6075)
+    spacing = 0.5 * math.sqrt(area / P) * scale_mult
+    M = (sh_degree + 1) ** 2
+    shs = np.zeros((P, M, 3))
+    shs[:, 0, :] = (rng.uniform(0, 1, (P, 3)) - 0.5) / SH_C0
+    if M > 1:
+        shs[:, 1:, :] = rng.normal(0, 0.3, (P, M - 1, 3))
+    s = dict(
+        means3D=xyz,
+        scales=np.exp(rng.normal(math.log(spacing), 0.3, (P, 3))),
+        rotations=_quat(rng, P),
+        opacities=_sigmoid(rng.standard_normal((P, 1))),
+        shs=shs, sh_degree=sh_degree, bg=np.ones(3),
+        camera=make_camera(W, H, 0.35, 0.35, T=[0, 0, 1.25]),
+        name=f"config2: {P} head-surface Gaussians, {W}x{H}, SH{sh_degree}",
+    )
+    return _f32(s)
+
+
+def stress_scene(seed=0, P=500000, W=1024, H=1024, view=0, n_views=72):
+    """BASELINE config 5: 500k Gaussians, SH degree 3, 1024x1024, orbit view `view` of `n_views`; 5 % of the
+    splats are large (stresses tile rectangles, per-tile list length and the large-tile sort path)."""
+    rng = np.random.default_rng(seed)
+    xyz = head_points(rng, P) * 4.0  # object ~0.9 m wide seen from 2.5 m
+    base = 0.5 * math.sqrt(4 * math.pi * 0.45 ** 2 / P)
+    log_s = rng.normal(math.log(base), 0.4, (P, 3))
+    big = rng.uniform(size=P) < 0.05
+    log_s[big] += math.log(8.0)
+    shs = np.zeros((P, 16, 3))
+    shs[:, 0, :] = (rng.uniform(0, 1, (P, 3)) - 0.5) / SH_C0
+    shs[:, 1:, :] = rng.normal(0, 0.3, (P, 15, 3))
+    s = dict(
+        means3D=xyz, scales=np.exp(log_s), rotations=_quat(rng, P),
+        opacities=_sigmoid(rng.standard_normal((P, 1))), shs=shs, sh_degree=3, bg=np.zeros(3),
+        camera=orbit_camera(W, H, 0.35, view, n_views, radius=2.5),
+        name=f"config5: {P} Gaussians, {W}x{H}, SH3, orbit view {view}/{n_views}",
+    )
+    return _f32(s)
+
+
+def _f32(s):
+    for k, v in list(s.items()):
+        if isinstance(v, np.ndarray):
+            s[k] = np.ascontiguousarray(v, dtype=np.float32)
+    return s
+
+
+def to_torch(scene, device):
+    """Scene dict -> torch tensors on `device` + a GaussianRasterizationSettings-ready camera dict."""
+    import torch
+
+    out = {}
+    for k, v in scene.items():
+        if isinstance(v, np.ndarray):
+            out[k] = torch.from_numpy(v).to(device)
+        elif isinstance(v, dict):
+            out[k] = {kk: (torch.from_numpy(vv).to(device) if isinstance(vv, np.ndarray) else vv) for kk, vv in v.items()}
+        else:
+            out[k] = v
+    return out

@@ -1,0 +1,129 @@
+/*
+ * fatesplat.h -- C ABI of libfatesplat.so, the sm_100a 3D-Gaussian-splatting renderer that replaces the
+ * native side of FateAvatar's rasterizer operators.
+ *
+ * Boundary being replaced (reference = /root/reference/submodules/diff-gaussian-rasterization, "DGR", and
+ * /root/reference/submodules/simple-knn):
+ *
+ *   fs_forward        <- CudaRasterizer::Rasterizer::forward   DGR cuda_rasterizer/rasterizer.h:35-59,
+ *                        rasterizer_impl.cu:198-336; bound to Python by RasterizeGaussiansCUDA,
+ *                        DGR rasterize_points.cu:35-115 (pybind: ext.cpp:15)
+ *   fs_backward       <- CudaRasterizer::Rasterizer::backward  DGR rasterizer.h:61-85, rasterizer_impl.cu:340-434;
+ *                        RasterizeGaussiansBackwardCUDA, rasterize_points.cu:117-196 (ext.cpp:16)
+ *   fs_mark_visible   <- CudaRasterizer::Rasterizer::markVisible DGR rasterizer.h:28-33, rasterizer_impl.cu:141-154;
+ *                        markVisible, rasterize_points.cu:198-217 (ext.cpp:17)
+ *   fs_knn_mean_dist2 <- SimpleKNN::knn  simple-knn/simple_knn.h, simple_knn.cu:186-222; distCUDA2, spatial.cu:15-26
+ *
+ * Differences from the reference native surface, all deliberate:
+ *   - plain C, raw device pointers and sizes, explicit stream, no torch/glm/std::function types;
+ *   - the three growable scratch buffers (geom/binning/img, DGR rasterize_points.cu:68-78) are ONE
+ *     caller-owned workspace whose size comes from fs_workspace_bytes(); the library never allocates;
+ *   - no host synchronisation: num_rendered is written to the workspace header on the device and, if the
+ *     caller passes a pinned host pointer, copied there asynchronously on `stream`;
+ *   - every call returns a status (0 = ok, <0 = error; text via fs_last_error()) instead of throwing.
+ *
+ * All pointers named `d_*` are device pointers; absent optional inputs are NULL exactly where the
+ * reference receives an empty tensor (rasterize_points.cu:97-103).  Matrices are the 16 floats of the
+ * reference's *transposed* view / full-projection tensors (points are row vectors).
+ */
+#ifndef FATESPLAT_H
+#define FATESPLAT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FS_OK 0
+#define FS_ERR_INVALID_ARGUMENT (-1)
+#define FS_ERR_WORKSPACE_TOO_SMALL (-2)
+#define FS_ERR_CUDA (-3)
+#define FS_ERR_UNSUPPORTED (-4)
+
+/* Header at byte 0 of the workspace (device memory).  fs_forward also mirrors it to `h_info` (pinned). */
+typedef struct fs_frame_info {
+    uint32_t num_rendered; /* R: number of (Gaussian, tile) instances, == reference's return value          */
+    uint32_t overflow;     /* 1 if R exceeded the workspace's instance capacity (frame is incomplete)       */
+    uint32_t num_visible;  /* Gaussians with radii > 0                                                      */
+    uint32_t max_tile_instances; /* heaviest tile's instance count                                         */
+    uint32_t reserved[4];
+} fs_frame_info;
+
+/* Byte offsets (from the workspace base) of the named per-frame arrays: the parity taps.
+ * They play the role of GeometryState / BinningState / ImageState (DGR rasterizer_impl.h:30-66). */
+typedef struct fs_workspace_layout {
+    size_t total_bytes;
+    size_t info;          /* fs_frame_info                                                   */
+    size_t depths;        /* float  [P]                                                      */
+    size_t cov3D;         /* float  [P][6]                                                   */
+    size_t splat;         /* float4 [P][3]: {mx,my,ex,ey} {conic.x,conic.y,conic.z,opacity} {r,g,b,bits(gaussian id)} */
+    size_t clamped;       /* uint8  [P][4] (3 used: SH colour clamp flags)                   */
+    size_t rect;          /* uint16 [P][4] (x0,y0,x1,y1) tile rectangle                      */
+    size_t tiles_touched; /* uint32 [P]                                                      */
+    size_t tile_count;    /* uint32 [Tn]                                                     */
+    size_t tile_cursor;   /* uint32 [Tn]                                                     */
+    size_t ranges;        /* uint32 [Tn][2]  (start,end) into point_list; (0,0) if empty     */
+    size_t big_tiles;     /* uint32 [Tn+1]   [0]=count, then ids of tiles too large for the smem sort */
+    size_t inst_keys;     /* uint64 [Rcap]   (depth_bits<<32 | gaussian) per tile segment    */
+    size_t inst_keys_alt; /* uint64 [Rcap]   ping-pong for the large-tile global sort        */
+    size_t point_list;    /* uint32 [Rcap]   sorted Gaussian ids (== reference point_list)   */
+    size_t inst_splat;    /* float4 [Rcap][3] splat records gathered in sorted order         */
+    size_t final_T;       /* float  [H*W]                                                    */
+    size_t n_contrib;     /* uint32 [H*W]                                                    */
+    size_t grad_acc;      /* float  [P][12]  backward accumulator: dmean2D.xy, dconic.xyw, dopacity, drgb, 3 pad */
+    size_t instance_capacity; /* Rcap (count, not bytes)                                     */
+} fs_workspace_layout;
+
+/* Size/layout of the workspace for P Gaussians, a W x H image and room for `instance_capacity` instances. */
+size_t fs_workspace_bytes(int P, int width, int height, size_t instance_capacity);
+int fs_get_workspace_layout(int P, int width, int height, size_t instance_capacity, fs_workspace_layout* out);
+
+/*
+ * Forward render.  Argument meaning and order follow Rasterizer::forward (rasterizer.h:35-59).
+ *   d_out_color [3][H][W], d_radii [P] (int32) are outputs owned by the caller.
+ *   h_info: optional pinned host pointer; receives the frame header asynchronously on `stream`.
+ * Empty input (P == 0) leaves out_color untouched like the reference (rasterize_points.cu:81).
+ */
+int fs_forward(int P, int D, int M, const float* d_background, int width, int height, const float* d_means3D,
+               const float* d_shs, const float* d_colors_precomp, const float* d_opacities, const float* d_scales,
+               float scale_modifier, const float* d_rotations, const float* d_cov3D_precomp,
+               const float* d_viewmatrix, const float* d_projmatrix, const float* d_cam_pos, float tan_fovx,
+               float tan_fovy, int prefiltered, float* d_out_color, int* d_radii, void* d_workspace,
+               size_t workspace_bytes, size_t instance_capacity, fs_frame_info* h_info, void* stream);
+
+/*
+ * Backward.  Argument meaning follows Rasterizer::backward (rasterizer.h:61-85).  The workspace must be the
+ * one fs_forward filled for the same inputs.  All dL_* outputs are [P,...] and are fully written
+ * (zero for culled Gaussians) -- the caller does not need to zero-fill them.
+ *   d_dL_dmean2D [P][3] (z = 0), d_dL_dcolors [P][3], d_dL_dopacity [P], d_dL_dmean3D [P][3],
+ *   d_dL_dcov3D [P][6], d_dL_dsh [P][M][3], d_dL_dscale [P][3], d_dL_drot [P][4].
+ */
+int fs_backward(int P, int D, int M, const float* d_background, int width, int height, const float* d_means3D,
+                const float* d_shs, const float* d_colors_precomp, const float* d_scales, float scale_modifier,
+                const float* d_rotations, const float* d_cov3D_precomp, const float* d_viewmatrix,
+                const float* d_projmatrix, const float* d_cam_pos, float tan_fovx, float tan_fovy,
+                const int* d_radii, void* d_workspace, size_t workspace_bytes, size_t instance_capacity,
+                const float* d_dL_dpix, float* d_dL_dmean2D, float* d_dL_dopacity, float* d_dL_dcolors,
+                float* d_dL_dmean3D, float* d_dL_dcov3D, float* d_dL_dsh, float* d_dL_dscale, float* d_dL_drot,
+                void* stream);
+
+/* present[i] = (view-space z of means3D[i] > 0.2); uint8 0/1 (rasterizer_impl.cu:54-66). */
+int fs_mark_visible(int P, const float* d_means3D, const float* d_viewmatrix, const float* d_projmatrix,
+                    uint8_t* d_present, void* stream);
+
+/* Mean squared distance to the 3 nearest neighbours (simple_knn.cu:148-222). */
+size_t fs_knn_workspace_bytes(int P);
+int fs_knn_mean_dist2(int P, const float* d_points, float* d_mean_dist2, void* d_workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* Number of kernels the last fs_forward / fs_backward / fs_knn_mean_dist2 call on this thread launched. */
+int fs_last_launch_count(void);
+const char* fs_last_error(void);
+const char* fs_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FATESPLAT_H */
