@@ -24,8 +24,8 @@ class FsFrameInfo(C.Structure):
 
 _LAYOUT_FIELDS = [
     "total_bytes", "info", "depths", "cov3D", "splat", "clamped", "rect", "tiles_touched", "tile_count",
-    "tile_cursor", "ranges", "big_tiles", "inst_keys", "inst_keys_alt", "point_list", "inst_splat", "final_T",
-    "n_contrib", "grad_acc", "instance_capacity",
+    "tile_cursor", "ranges", "big_tiles", "work_order", "inst_keys", "inst_keys_alt", "point_list", "inst_splat", "final_T",
+    "n_contrib", "bwd_counter", "grad_acc", "instance_capacity",
 ]
 
 
@@ -37,7 +37,11 @@ class FsWorkspaceLayout(C.Structure):
 EXPORTS = [
     "fs_workspace_bytes", "fs_get_workspace_layout", "fs_forward", "fs_backward", "fs_mark_visible",
     "fs_knn_workspace_bytes", "fs_knn_mean_dist2", "fs_last_launch_count", "fs_last_error", "fs_version",
+    "fs_profile_enable", "fs_profile_read",
 ]
+
+STAGES = ["preprocess", "tile_scan", "scatter", "tile_sort", "big_tile_sort", "blend_forward", "blend_backward",
+          "preprocess_backward", "knn"]
 
 _lib = None
 
@@ -74,6 +78,10 @@ def load():
     lib.fs_knn_workspace_bytes.argtypes = [i]
     lib.fs_knn_mean_dist2.restype = i
     lib.fs_knn_mean_dist2.argtypes = [i, vp, vp, vp, sz, vp]
+    lib.fs_profile_enable.restype = None
+    lib.fs_profile_enable.argtypes = [i]
+    lib.fs_profile_read.restype = i
+    lib.fs_profile_read.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int), i]
     lib.fs_last_launch_count.restype = i
     lib.fs_last_error.restype = C.c_char_p
     lib.fs_version.restype = C.c_char_p
@@ -90,3 +98,12 @@ def workspace_layout(P, W, H, capacity):
     L = FsWorkspaceLayout()
     check(load().fs_get_workspace_layout(int(P), int(W), int(H), int(capacity), C.byref(L)), "fs_get_workspace_layout")
     return L
+
+
+def profile_read():
+    """{stage: (total_ms, launches)} accumulated since the last read (see fs_profile_enable)."""
+    n = len(STAGES)
+    ms = (C.c_float * n)()
+    cnt = (C.c_int * n)()
+    check(load().fs_profile_read(ms, cnt, n), "fs_profile_read")
+    return {STAGES[k]: (float(ms[k]), int(cnt[k])) for k in range(n)}

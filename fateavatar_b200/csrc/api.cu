@@ -37,6 +37,62 @@ void fs_set_error(const char* fmt, ...) {
 }
 void fs_count_launch(int n) { g_launches += n; }
 
+#include <cstdlib>
+#include <map>
+#include <string>
+int fs_tuning(const char* env_name, int default_value) {
+    static std::map<std::string, int> cache;
+    auto it = cache.find(env_name);
+    if (it != cache.end()) return it->second;
+    const char* v = getenv(env_name);
+    const int val = v ? atoi(v) : default_value;
+    cache[env_name] = val;
+    return val;
+}
+
+// ---- per-stage profiling ----------------------------------------------------------------------------------
+#include <vector>
+namespace {
+struct ProfRec {
+    int stage;
+    cudaEvent_t start, stop;
+};
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+std::vector<cudaEvent_t> g_event_pool;
+cudaEvent_t prof_event() {
+    if (!g_event_pool.empty()) {
+        cudaEvent_t e = g_event_pool.back();
+        g_event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+}  // namespace
+
+FsStageTimer::FsStageTimer(int stage, cudaStream_t st) : slot(-1), stream(st) {
+    if (!g_prof_on) return;
+    ProfRec r{stage, prof_event(), prof_event()};
+    cudaEventRecord(r.start, stream);
+    g_prof.push_back(r);
+    slot = (int)g_prof.size() - 1;
+}
+FsStageTimer::~FsStageTimer() {
+    if (slot >= 0) cudaEventRecord(g_prof[slot].stop, stream);
+}
+
+int fs_num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 void fs_compute_layout(int P, int W, int H, size_t Rcap, fs_workspace_layout* L) {
@@ -50,10 +106,11 @@ void fs_compute_layout(int P, int W, int H, size_t Rcap, fs_workspace_layout* L)
     };
     memset(L, 0, sizeof(*L));
     L->info = take(sizeof(fs_frame_info));
-    L->tile_count = take(Tn * 4);  // directly after the header: one memset clears both
-    L->tile_cursor = take(Tn * 4);
+    L->tile_count = take(Tn * 4 * FS_CNT_STRIDE);  // directly after the header: one memset clears both
+    L->tile_cursor = take(Tn * 4 * FS_CNT_STRIDE);
     L->ranges = take(Tn * 8);
     L->big_tiles = take((Tn + 1) * 4);
+    L->work_order = take(Tn * 4);
     L->depths = take(Pn * 4);
     L->cov3D = take(Pn * 24);
     L->splat = take(Pn * 48);
@@ -66,6 +123,7 @@ void fs_compute_layout(int P, int W, int H, size_t Rcap, fs_workspace_layout* L)
     L->inst_splat = take(Rcap * 48);
     L->final_T = take((size_t)W * H * 4);
     L->n_contrib = take((size_t)W * H * 4);
+    L->bwd_counter = take(256);
     L->grad_acc = take(Pn * 48);
     L->instance_capacity = Rcap;
     L->total_bytes = off;
@@ -228,6 +286,31 @@ int fs_knn_mean_dist2(int P, const float* d_points, float* d_mean_dist2, void* d
                                  static_cast<cudaStream_t>(stream));
     if (rc != FS_OK) return rc;
     FS_CUDA_CHECK(cudaGetLastError());
+    return FS_OK;
+}
+
+void fs_profile_enable(int on) { g_prof_on = on != 0; }
+
+int fs_profile_read(float* total_ms, int* counts, int n) {
+    for (int i = 0; i < n; ++i) {
+        total_ms[i] = 0.0f;
+        counts[i] = 0;
+    }
+    for (auto& r : g_prof) {
+        if (cudaEventSynchronize(r.stop) != cudaSuccess) {
+            fs_set_error("fs_profile_read: event sync failed");
+            return FS_ERR_CUDA;
+        }
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, r.start, r.stop);
+        if (r.stage < n) {
+            total_ms[r.stage] += ms;
+            counts[r.stage] += 1;
+        }
+        g_event_pool.push_back(r.start);
+        g_event_pool.push_back(r.stop);
+    }
+    g_prof.clear();
     return FS_OK;
 }
 

@@ -30,100 +30,123 @@ __device__ const float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.
                                    0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
                                    -0.5900435899266435f};
 
-constexpr int kThreads = 256;
-constexpr int kBatch = 256;
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__device__ __forceinline__ float warp_sum(float v) {
+// One step of a transposing warp reduction: N live values -> N/2, pairing lanes that differ in bit OFF.
+// The lane with the bit set keeps the upper half.  After steps 16, 8, 4 on 32 values every lane holds the
+// 4 values {i + (lane & 28)}, summed over its 8-lane class; two plain xor steps finish the sum.
+template <int OFF, int N>
+__device__ __forceinline__ void treduce_step(float* v, int lane) {
+    const bool up = (lane & OFF) != 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+    for (int i = 0; i < N / 2; ++i) {
+        const float send = up ? v[i] : v[i + N / 2];
+        const float keep = up ? v[i + N / 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+    }
 }
+
+constexpr int kGroup = 4;
 
 // grad_acc layout per Gaussian (12 floats): [0]=dmean2D.x [1]=dmean2D.y [2]=dconic.x [3]=dconic.y
 //                                           [4]=dconic.w  [5]=dopacity  [6..8]=dcolor rgb  [9..11]=0
-__global__ void __launch_bounds__(kThreads)
-blend_backward_kernel(const uint2* __restrict__ ranges, const SplatRec* __restrict__ inst_splat, int W, int H,
-                      const float* __restrict__ bg_color, const float* __restrict__ final_T,
-                      const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpix,
-                      float* __restrict__ grad_acc, uint32_t Rcap) {
-    __shared__ __align__(128) SplatRec s_rec[2][kBatch];
-    __shared__ __align__(16) float s_grad[kBatch * 9];
-    __shared__ __align__(8) uint64_t s_full[2];
-    __shared__ uint32_t s_last[8];
+constexpr int kWarps = 8;   // independent warps per CTA
+constexpr int kBatch = 64;  // records per stage
+struct WarpStage {
+    SplatRec rec[2][kBatch];
+};
 
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int gx = (W + FS_TILE - 1) / FS_TILE;
-    const int tile = blockIdx.x;
-    const int tile_x = tile % gx, tile_y = tile / gx;
-    const int bx = tile_x * FS_TILE + (wid & 1) * 8, by = tile_y * FS_TILE + (wid >> 1) * 4;
-    const int px = bx + (lane & 7), py = by + (lane >> 3);
-    const bool inside = px < W && py < H;
-    const float pxf = (float)px, pyf = (float)py;
-    const float wx0 = (float)bx, wx1 = (float)min(bx + 7, W - 1), wy0 = (float)by, wy1 = (float)min(by + 3, H - 1);
+// Persistent warps pull (tile, 8x4 block) units heaviest-first, exactly like the forward kernel.
+__global__ void __launch_bounds__(kWarps * 32)
+blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ work_order,
+                      const uint32_t* __restrict__ n_nonempty_tiles, uint32_t* __restrict__ work_counter,
+                      const SplatRec* __restrict__ inst_splat, int W, int H, const float* __restrict__ bg_color,
+                      const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
+                      const float* __restrict__ dL_dpix, float* __restrict__ grad_acc, uint32_t Rcap) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    WarpStage* stages = reinterpret_cast<WarpStage*>(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sizeof(WarpStage) * kWarps);
 
-    uint2 range = ranges[tile];
-    if (range.y > Rcap) range = make_uint2(0u, 0u);
-    if (range.y == range.x) return;
-
-    const size_t pid = (size_t)py * W + px, plane = (size_t)H * W;
-    const float T_final = inside ? final_T[pid] : 0.0f;
-    const uint32_t last_contributor = inside ? n_contrib[pid] : 0u;
-    float dpx = 0.f, dpy = 0.f, dpz = 0.f;
-    if (inside) {
-        dpx = dL_dpix[pid];
-        dpy = dL_dpix[plane + pid];
-        dpz = dL_dpix[2 * plane + pid];
-    }
-    const float bg_dot = __ldg(bg_color) * dpx + __ldg(bg_color + 1) * dpy + __ldg(bg_color + 2) * dpz;
-    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
-
-    // positions >= max n_contrib of the CTA are never visited: start there
-    uint32_t wl = last_contributor;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wl = max(wl, __shfl_xor_sync(0xffffffffu, wl, o));
-    const uint32_t warp_last = wl;
-    if (lane == 0) s_last[wid] = wl;
-    for (int i = tid; i < kBatch * 9; i += kThreads) s_grad[i] = 0.0f;
-    if (tid == 0) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    SplatRec(*rec_ring)[kBatch] = stages[wid].rec;
+    uint64_t* s_full = bars + wid * 2;
+    if (lane == 0) {
         fs::mbar_init(&s_full[0], 1);
         fs::mbar_init(&s_full[1], 1);
         fs::mbar_fence_init();
     }
-    __syncthreads();
-    uint32_t cta_last = 0;
+    __syncwarp();
+    uint32_t fills = 0;
+
+    const int gx = (W + FS_TILE - 1) / FS_TILE;
+    const float bg0 = __ldg(bg_color), bg1 = __ldg(bg_color + 1), bg2 = __ldg(bg_color + 2);
+    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+    const uint32_t n_units = __ldg(n_nonempty_tiles) * 8u;
+    const size_t plane = (size_t)H * W;
+
+    for (;;) {
+        uint32_t unit = 0;
+        if (lane == 0) unit = atomicAdd(work_counter, 1u);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= n_units) break;
+        const int tile = (int)work_order[unit >> 3];
+        const int blk = (int)(unit & 7u);
+        const int tile_x = tile % gx, tile_y = tile / gx;
+        const int bx = tile_x * FS_TILE + (blk & 1) * 8, by = tile_y * FS_TILE + (blk >> 1) * 4;
+        const int px = bx + (lane & 7), py = by + (lane >> 3);
+        const bool inside = px < W && py < H;
+        const float pxf = (float)px, pyf = (float)py;
+        const float wx0 = (float)bx, wx1 = (float)min(bx + 7, W - 1), wy0 = (float)by, wy1 = (float)min(by + 3, H - 1);
+
+        uint2 range = ranges[tile];
+        if (range.y > Rcap) range = make_uint2(0u, 0u);
+
+        const size_t pid = (size_t)py * W + px;
+        const float T_final = inside ? final_T[pid] : 0.0f;
+        const uint32_t last_contributor = inside ? n_contrib[pid] : 0u;
+        float dpx = 0.f, dpy = 0.f, dpz = 0.f;
+        if (inside) {
+            dpx = dL_dpix[pid];
+            dpy = dL_dpix[plane + pid];
+            dpz = dL_dpix[2 * plane + pid];
+        }
+        const float bg_dot = bg0 * dpx + bg1 * dpy + bg2 * dpz;
+
+        // positions >= the block's largest n_contrib are never visited: the stream starts there
+        uint32_t wl = last_contributor;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) cta_last = max(cta_last, s_last[w]);
-    if (cta_last == 0) return;
-    const int nbatches = (int)((cta_last + kBatch - 1) / kBatch);
+        for (int o = 16; o > 0; o >>= 1) wl = max(wl, __shfl_xor_sync(0xffffffffu, wl, o));
+        const uint32_t warp_last = min(wl, range.y - range.x);
+        const int nbatches = (int)((warp_last + kBatch - 1) / kBatch);
 
-    // batch k covers positions [lo_k, lo_k + cnt_k), walking down from cta_last
-    auto batch_lo = [&](int k) { return (uint32_t)max(0, (int)cta_last - (k + 1) * kBatch); };
-    auto batch_cnt = [&](int k) { return (cta_last - (uint32_t)k * kBatch) - batch_lo(k); };
-    auto issue = [&](int k) {
-        const uint32_t bytes = batch_cnt(k) * (uint32_t)sizeof(SplatRec);
-        fs::mbar_expect_tx(&s_full[k & 1], bytes);
-        fs::bulk_g2s(&s_rec[k & 1][0], inst_splat + range.x + batch_lo(k), bytes, &s_full[k & 1]);
-    };
-    if (tid == 0) issue(0);
+        // batch k covers positions [lo_k, lo_k + cnt_k), walking down from warp_last
+        auto batch_lo = [&](int k) { return (uint32_t)max(0, (int)warp_last - (k + 1) * kBatch); };
+        auto batch_cnt = [&](int k) { return (warp_last - (uint32_t)k * kBatch) - batch_lo(k); };
+        auto issue = [&](int k) {  // lane 0 only
+            const uint32_t bytes = batch_cnt(k) * (uint32_t)sizeof(SplatRec);
+            const uint32_t s = (fills + (uint32_t)k) & 1u;
+            fs::mbar_expect_tx(&s_full[s], bytes);
+            fs::bulk_g2s(&rec_ring[s][0], inst_splat + range.x + batch_lo(k), bytes, &s_full[s]);
+        };
+        if (lane == 0 && nbatches > 0) issue(0);
 
-    float T = T_final;
-    float ar0 = 0.f, ar1 = 0.f, ar2 = 0.f;  // accum_rec
-    float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;  // last_color
-    float last_alpha = 0.f;
+        float T = T_final;
+        float ar0 = 0.f, ar1 = 0.f, ar2 = 0.f;  // accum_rec
+        float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;  // last_color
+        float last_alpha = 0.f;
 
-    for (int k = 0; k < nbatches; ++k) {
-        if (tid == 0 && k + 1 < nbatches) issue(k + 1);
-        fs::mbar_wait(&s_full[k & 1], (uint32_t)(k >> 1) & 1u);
-        const SplatRec* rec = s_rec[k & 1];
-        const uint32_t lo = batch_lo(k);
-        const int cnt = (int)batch_cnt(k);
-        if (lo < warp_last) {  // otherwise nothing in this batch is visible to this warp's pixels
+        for (int kb = 0; kb < nbatches; ++kb) {
+            __syncwarp();
+            if (lane == 0 && kb + 1 < nbatches) issue(kb + 1);
+            const uint32_t f = fills + (uint32_t)kb;
+            fs::mbar_wait(&s_full[f & 1u], (f >> 1) & 1u);
+            const SplatRec* rec = rec_ring[f & 1u];
+            const uint32_t lo = batch_lo(kb);
+            const int cnt = (int)batch_cnt(kb);
             for (int cb = ((cnt - 1) >> 5) << 5; cb >= 0; cb -= 32) {
-                if (lo + (uint32_t)cb >= warp_last) continue;
                 const int j = cb + lane;
                 bool hit = false;
                 if (j < cnt) {
@@ -133,94 +156,114 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const SplatRec* __restri
                 }
                 unsigned m = __ballot_sync(0xffffffffu, hit);
                 while (m) {
-                    const int bit = 31 - __clz(m);
-                    m &= ~(1u << bit);
-                    const int jj = cb + bit;
-                    const uint32_t pos = lo + (uint32_t)jj;
-                    float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f, g4 = 0.f, g5 = 0.f, g6 = 0.f, g7 = 0.f, g8 = 0.f;
-                    bool contrib = false;
-                    if (pos < last_contributor) {
-                        const float4 q0 = rec[jj].q0;
-                        const float4 q1 = rec[jj].q1;
-                        const float dx = fs::sub(q0.x, pxf), dy = fs::sub(q0.y, pyf);
-                        const float power = fs::splat_power(dx, dy, q1.x, q1.y, q1.z);
-                        if (power <= 0.0f) {
-                            const float G = expf(power);
-                            const float alpha = fminf(0.99f, fs::mul(q1.w, G));
-                            if (alpha >= 1.0f / 255.0f) {
-                                contrib = true;
-                                const float4 q2 = rec[jj].q2;
-                                const float one_m_alpha = 1.0f - alpha;
-                                T = __fdiv_rn(T, one_m_alpha);
-                                const float dchannel_dcolor = alpha * T;
-                                const float one_m_la = 1.0f - last_alpha;
-                                ar0 = last_alpha * lc0 + one_m_la * ar0;
-                                ar1 = last_alpha * lc1 + one_m_la * ar1;
-                                ar2 = last_alpha * lc2 + one_m_la * ar2;
-                                lc0 = q2.x;
-                                lc1 = q2.y;
-                                lc2 = q2.z;
-                                float dL_dalpha = (q2.x - ar0) * dpx + (q2.y - ar1) * dpy + (q2.z - ar2) * dpz;
-                                g6 = dchannel_dcolor * dpx;
-                                g7 = dchannel_dcolor * dpy;
-                                g8 = dchannel_dcolor * dpz;
-                                dL_dalpha *= T;
-                                last_alpha = alpha;
-                                dL_dalpha += (-T_final / one_m_alpha) * bg_dot;
-                                const float dL_dG = q1.w * dL_dalpha;
-                                const float gdx = G * dx, gdy = G * dy;
-                                const float dG_ddelx = -gdx * q1.x - gdy * q1.y;
-                                const float dG_ddely = -gdy * q1.z - gdx * q1.y;
-                                g0 = dL_dG * dG_ddelx * ddelx_dx;
-                                g1 = dL_dG * dG_ddely * ddely_dy;
-                                g2 = -0.5f * gdx * dx * dL_dG;
-                                g3 = -0.5f * gdx * dy * dL_dG;
-                                g4 = -0.5f * gdy * dy * dL_dG;
-                                g5 = G * dL_dalpha;
-                            }
-                        }
+                    // four survivors per round, back to front
+                    int jj[kGroup];
+                    bool live[kGroup];
+#pragma unroll
+                    for (int k = 0; k < kGroup; ++k) {  // branch-free extraction, highest set bit first
+                        const int bit = 31 - __clz(m);    // -1 when m == 0
+                        live[k] = bit >= 0;
+                        jj[k] = live[k] ? cb + bit : cb;
+                        m &= ~(live[k] ? (1u << bit) : 0u);
                     }
-                    if (__any_sync(0xffffffffu, contrib)) {
-                        g0 = warp_sum(g0);
-                        g1 = warp_sum(g1);
-                        g2 = warp_sum(g2);
-                        g3 = warp_sum(g3);
-                        g4 = warp_sum(g4);
-                        g5 = warp_sum(g5);
-                        g6 = warp_sum(g6);
-                        g7 = warp_sum(g7);
-                        g8 = warp_sum(g8);
-                        float v = g0;
-                        v = lane == 1 ? g1 : v;
-                        v = lane == 2 ? g2 : v;
-                        v = lane == 3 ? g3 : v;
-                        v = lane == 4 ? g4 : v;
-                        v = lane == 5 ? g5 : v;
-                        v = lane == 6 ? g6 : v;
-                        v = lane == 7 ? g7 : v;
-                        v = lane == 8 ? g8 : v;
-                        if (lane < 9) atomicAdd(&s_grad[jj * 9 + lane], v);
+                    // independent part: power, G, alpha for the four survivors
+                    float G[kGroup], alpha[kGroup], dx[kGroup], dy[kGroup], inv[kGroup];
+                    float4 q1[kGroup], q2[kGroup];
+                    bool ok[kGroup];
+                    bool any_ok = false;
+#pragma unroll
+                    for (int k = 0; k < kGroup; ++k) {
+                        const int r = jj[k];
+                        const float4 q0 = rec[r].q0;
+                        q1[k] = rec[r].q1;
+                        q2[k] = rec[r].q2;
+                        dx[k] = fs::sub(q0.x, pxf);
+                        dy[k] = fs::sub(q0.y, pyf);
+                        const float power = fs::splat_power(dx[k], dy[k], q1[k].x, q1[k].y, q1[k].z);
+                        G[k] = expf(power);
+                        alpha[k] = fminf(0.99f, fs::mul(q1[k].w, G[k]));
+                        ok[k] = live[k] && (lo + (uint32_t)r) < last_contributor && power <= 0.0f &&
+                                alpha[k] >= 1.0f / 255.0f;
+                        inv[k] = __fdividef(1.0f, 1.0f - alpha[k]);
+                        any_ok |= ok[k];
+                    }
+                    if (!__any_sync(0xffffffffu, any_ok)) continue;
+                    // sequential part: transmittance and the running "colour behind" recurrence
+                    float Tk[kGroup], a0[kGroup], a1[kGroup], a2[kGroup];
+#pragma unroll
+                    for (int k = 0; k < kGroup; ++k) {
+                        {   // predicated: no branches inside the dependent chain
+                            const float oml = 1.0f - last_alpha;
+                            const float n0 = last_alpha * lc0 + oml * ar0;
+                            const float n1 = last_alpha * lc1 + oml * ar1;
+                            const float n2 = last_alpha * lc2 + oml * ar2;
+                            T = ok[k] ? T * inv[k] : T;
+                            ar0 = ok[k] ? n0 : ar0;
+                            ar1 = ok[k] ? n1 : ar1;
+                            ar2 = ok[k] ? n2 : ar2;
+                            lc0 = ok[k] ? q2[k].x : lc0;
+                            lc1 = ok[k] ? q2[k].y : lc1;
+                            lc2 = ok[k] ? q2[k].z : lc2;
+                            last_alpha = ok[k] ? alpha[k] : last_alpha;
+                        }
+                        Tk[k] = T;
+                        a0[k] = ar0;
+                        a1[k] = ar1;
+                        a2[k] = ar2;
+                    }
+                    // independent part: the nine partial derivatives per survivor
+                    float v[32], e[kGroup];
+#pragma unroll
+                    for (int k = 0; k < kGroup; ++k) {
+                        const float w = ok[k] ? 1.0f : 0.0f;
+                        const float dchannel_dcolor = alpha[k] * Tk[k] * w;
+                        float dL_dalpha = ((q2[k].x - a0[k]) * dpx + (q2[k].y - a1[k]) * dpy + (q2[k].z - a2[k]) * dpz) * Tk[k];
+                        dL_dalpha += (-T_final * inv[k]) * bg_dot;
+                        dL_dalpha *= w;
+                        const float dL_dG = q1[k].w * dL_dalpha;
+                        const float gdx = G[k] * dx[k], gdy = G[k] * dy[k];
+                        const float dG_ddelx = -gdx * q1[k].x - gdy * q1[k].y;
+                        const float dG_ddely = -gdy * q1[k].z - gdx * q1[k].y;
+                        v[k * 8 + 0] = dL_dG * dG_ddelx * ddelx_dx;
+                        v[k * 8 + 1] = dL_dG * dG_ddely * ddely_dy;
+                        v[k * 8 + 2] = -0.5f * gdx * dx[k] * dL_dG;
+                        v[k * 8 + 3] = -0.5f * gdx * dy[k] * dL_dG;
+                        v[k * 8 + 4] = -0.5f * gdy * dy[k] * dL_dG;
+                        v[k * 8 + 5] = G[k] * dL_dalpha;
+                        v[k * 8 + 6] = dchannel_dcolor * dpx;
+                        v[k * 8 + 7] = dchannel_dcolor * dpy;
+                        e[k] = dchannel_dcolor * dpz;
+                    }
+                    // transposing warp reduction: 36 values x 32 lanes in 42 shuffles (naive: 180)
+                    treduce_step<16, 32>(v, lane);
+                    treduce_step<8, 16>(v, lane);
+                    treduce_step<4, 8>(v, lane);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        v[i] += __shfl_xor_sync(0xffffffffu, v[i], 2);
+                        v[i] += __shfl_xor_sync(0xffffffffu, v[i], 1);
+                    }
+                    treduce_step<16, 4>(e, lane);
+                    treduce_step<8, 2>(e, lane);
+                    e[0] += __shfl_xor_sync(0xffffffffu, e[0], 4);
+                    e[0] += __shfl_xor_sync(0xffffffffu, e[0], 2);
+                    e[0] += __shfl_xor_sync(0xffffffffu, e[0], 1);
+                    // lane (l & 3) == 0 owns values {(l & 28) .. +3} = survivor l>>3, half (l>>2)&1;
+                    // lane (l & 7) == 0 also owns that survivor's ninth value
+                    const int ks = lane >> 3;
+                    const int js = ks == 0 ? jj[0] : ks == 1 ? jj[1] : ks == 2 ? jj[2] : jj[3];
+                    const bool ls = ks == 0 ? live[0] : ks == 1 ? live[1] : ks == 2 ? live[2] : live[3];
+                    if ((lane & 3) == 0 && ls) {
+                        const uint32_t g = __float_as_uint(rec[js].q2.w);
+                        float* dst = grad_acc + (size_t)g * 12;
+                        if (v[0] != 0.f || v[1] != 0.f || v[2] != 0.f || v[3] != 0.f)
+                            red_add_v4(dst + ((lane >> 2) & 1) * 4, v[0], v[1], v[2], v[3]);
+                        if ((lane & 7) == 0 && e[0] != 0.f) atomicAdd(dst + 8, e[0]);
                     }
                 }
             }
         }
-        __syncthreads();  // every warp is done with stage k&1 and with its shared accumulators
-        if (tid < cnt) {
-            float* sg = &s_grad[tid * 9];
-            const float a0 = sg[0], a1 = sg[1], a2 = sg[2], a3 = sg[3], a4 = sg[4], a5 = sg[5], a6 = sg[6], a7 = sg[7],
-                        a8 = sg[8];
-            if (a0 != 0.f || a1 != 0.f || a2 != 0.f || a3 != 0.f || a4 != 0.f || a5 != 0.f || a6 != 0.f || a7 != 0.f ||
-                a8 != 0.f) {
-                const uint32_t g = __float_as_uint(rec[tid].q2.w);
-                float* dst = grad_acc + (size_t)g * 12;
-                red_add_v4(dst, a0, a1, a2, a3);
-                red_add_v4(dst + 4, a4, a5, a6, a7);
-                atomicAdd(dst + 8, a8);
-#pragma unroll
-                for (int q = 0; q < 9; ++q) sg[q] = 0.0f;
-            }
-        }
-        __syncthreads();
+        fills += (uint32_t)nbatches;
     }
 }
 
@@ -452,15 +495,31 @@ void fs_launch_backward(int P, int D, int M, const float* bg, int W, int H, cons
                         float* dL_dsh, float* dL_dscale, float* dL_drot, cudaStream_t stream) {
     const int gx = (W + FS_TILE - 1) / FS_TILE, gy = (H + FS_TILE - 1) / FS_TILE;
     float* grad_acc = reinterpret_cast<float*>(ws + L.grad_acc);
-    cudaMemsetAsync(grad_acc, 0, (size_t)P * 48, stream);
-    blend_backward_kernel<<<gx * gy, kThreads, 0, stream>>>(
-        reinterpret_cast<const uint2*>(ws + L.ranges), reinterpret_cast<const SplatRec*>(ws + L.inst_splat), W, H, bg,
-        reinterpret_cast<const float*>(ws + L.final_T), reinterpret_cast<const uint32_t*>(ws + L.n_contrib), dL_dpix,
-        grad_acc, (uint32_t)L.instance_capacity);
+    // work counter (256-byte slot) and the per-Gaussian accumulator are contiguous: one memset node
+    cudaMemsetAsync(ws + L.bwd_counter, 0, (L.grad_acc - L.bwd_counter) + (size_t)P * 48, stream);
+    {
+        FsStageTimer timer(FS_STAGE_BLEND_BWD, stream);
+        const size_t smem = sizeof(WarpStage) * kWarps + sizeof(uint64_t) * 2 * kWarps;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(blend_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set = true;
+        }
+        auto* info = reinterpret_cast<fs_frame_info*>(ws + L.info);
+        const int ctas_per_sm = fs_tuning("FATESPLAT_BWD_CTAS_PER_SM", 1);
+        const int grid = min(fs_num_sms() * ctas_per_sm, (gx * gy * 8 + kWarps - 1) / kWarps);
+        blend_backward_kernel<<<grid, kWarps * 32, smem, stream>>>(
+            reinterpret_cast<const uint2*>(ws + L.ranges), reinterpret_cast<const uint32_t*>(ws + L.work_order),
+            &info->reserved[3], reinterpret_cast<uint32_t*>(ws + L.bwd_counter),
+            reinterpret_cast<const SplatRec*>(ws + L.inst_splat), W, H, bg,
+            reinterpret_cast<const float*>(ws + L.final_T), reinterpret_cast<const uint32_t*>(ws + L.n_contrib),
+            dL_dpix, grad_acc, (uint32_t)L.instance_capacity);
+    }
     const float h_y = H / (2.0f * tan_fovy);
     const float h_x = W / (2.0f * tan_fovx);
     const float* cov = cov3D_precomp ? cov3D_precomp : reinterpret_cast<const float*>(ws + L.cov3D);
     const float* sh_in = colors_precomp ? nullptr : shs;
+    FsStageTimer timer(FS_STAGE_PREPROCESS_BWD, stream);
     preprocess_backward_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
         P, D, M, means3D, radii, sh_in, reinterpret_cast<const uchar4*>(ws + L.clamped),
         cov3D_precomp ? nullptr : scales, rotations, scale_modifier, cov, viewmatrix, projmatrix, W, H, tan_fovx,

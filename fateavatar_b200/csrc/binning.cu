@@ -11,33 +11,42 @@
 // Sorting the composite 64-bit key (depth_bits<<32 | gaussian) per tile gives the identical unique order,
 // independent of the atomic scatter order => point_list and ranges are bit-exact.
 //
+// Per-tile sort: keys of one tile are spread over a narrow depth interval, so a linear bucket pass on the
+// depth bits (shared-memory atomics give each key its rank inside its bucket), an exclusive scan and a tiny
+// per-bucket insertion sort order the segment in O(n) work; pathological distributions (one bucket holding
+// most keys) fall back to a bitonic network.  Every path ends in the same total order on the 64-bit key.
+//
 // HBM traffic: 8*R (scatter) + 8*R + 4*R + 48*R (sort in/out + record gather) vs. the reference's 12*R emit +
 // 144*R sort + 8*R ranges.
 #include "common.cuh"
 
 namespace {
 
+typedef unsigned long long u64;
 constexpr int kScanThreads = 1024;
 
 // ---- K2: exclusive scan of per-tile counts; ranges; big-tile list; frame header ---------------------------
 __global__ void __launch_bounds__(kScanThreads)
 tile_scan_kernel(int Tn, const uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_cursor,
-                 uint2* __restrict__ ranges, uint32_t* __restrict__ big_tiles, fs_frame_info* __restrict__ info,
-                 uint32_t Rcap) {
+                 uint2* __restrict__ ranges, uint32_t* __restrict__ big_tiles, uint32_t* __restrict__ work_order,
+                 fs_frame_info* __restrict__ info, uint32_t Rcap) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_wmax[32];
     __shared__ uint32_t s_nbig;
+    __shared__ uint32_t s_bin[33];  // tiles per log2(count) class; class 0 = empty
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) s_nbig = 0;
+    if (tid < 33) s_bin[tid] = 0;
+    __syncthreads();
     const int per = (Tn + kScanThreads - 1) / kScanThreads;
     const int beg = min(Tn, tid * per), end = min(Tn, beg + per);
     uint32_t sum = 0, mx = 0;
     for (int t = beg; t < end; ++t) {
-        const uint32_t c = tile_count[t];
+        const uint32_t c = tile_count[(size_t)t * FS_CNT_STRIDE];
         sum += c;
         mx = max(mx, c);
+        atomicAdd(&s_bin[c ? 32 - __clz(c) : 0], 1u);
     }
-    // block exclusive scan of `sum`
     uint32_t incl = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -70,46 +79,62 @@ tile_scan_kernel(int Tn, const uint32_t* __restrict__ tile_count, uint32_t* __re
     __syncthreads();
     uint32_t off = s_warp[wid] + (incl - sum);
     for (int t = beg; t < end; ++t) {
-        const uint32_t c = tile_count[t];
-        tile_cursor[t] = off;
+        const uint32_t c = tile_count[(size_t)t * FS_CNT_STRIDE];
+        tile_cursor[(size_t)t * FS_CNT_STRIDE] = off;
         ranges[t] = c ? make_uint2(off, off + c) : make_uint2(0u, 0u);  // empty tiles stay (0,0) like the memset
         if (c > FS_SORT_SMEM_CAP) big_tiles[1 + atomicAdd(&s_nbig, 1u)] = (uint32_t)t;
         off += c;
     }
     __syncthreads();
-    if (tid == 0) big_tiles[0] = s_nbig;
+    if (tid == 0) {
+        big_tiles[0] = s_nbig;
+        info->reserved[3] = (uint32_t)Tn - s_bin[0];  // non-empty tiles (work units of the backward blend)
+        uint32_t o = 0;  // heaviest class first; s_bin becomes the running write cursor of each class
+        for (int b = 32; b >= 0; --b) {
+            const uint32_t n = s_bin[b];
+            s_bin[b] = o;
+            o += n;
+        }
+    }
+    __syncthreads();
+    for (int t = beg; t < end; ++t) {
+        const uint32_t c = tile_count[(size_t)t * FS_CNT_STRIDE];
+        work_order[atomicAdd(&s_bin[c ? 32 - __clz(c) : 0], 1u)] = (uint32_t)t;
+    }
 }
 
 // ---- K3: scatter (depth, gaussian) keys into tile segments -------------------------------------------------
 __global__ void __launch_bounds__(256)
 scatter_kernel(int P, int gx, const ushort4* __restrict__ rect, const float* __restrict__ depths,
-               uint32_t* __restrict__ tile_cursor, unsigned long long* __restrict__ keys, uint32_t Rcap) {
+               uint32_t* __restrict__ tile_cursor, u64* __restrict__ keys, uint32_t Rcap) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
     const ushort4 rc = rect[idx];
     if (rc.x >= rc.z || rc.y >= rc.w) return;
-    const unsigned long long key = ((unsigned long long)__float_as_uint(depths[idx]) << 32) | (uint32_t)idx;
+    const u64 key = ((u64)__float_as_uint(depths[idx]) << 32) | (uint32_t)idx;
     for (int y = rc.y; y < rc.w; ++y)
         for (int x = rc.x; x < rc.z; ++x) {
-            const uint32_t pos = atomicAdd(&tile_cursor[y * gx + x], 1u);
+            const uint32_t pos = atomicAdd(&tile_cursor[(size_t)(y * gx + x) * FS_CNT_STRIDE], 1u);
             if (pos < Rcap) keys[pos] = key;
         }
 }
 
 // ---- bitonic network with ascending-only compare-exchanges (virtual +inf padding needs no storage) --------
-template <typename KeyPtr>
-__device__ __forceinline__ void bitonic_sort_ascending(KeyPtr s, uint32_t n, int tid, int nthreads) {
+__device__ __forceinline__ void bitonic_sort_ascending(u64* s, uint32_t n, int tid, int nthreads) {
     if (n < 2) return;
-    uint32_t m = 1;
-    while (m < n) m <<= 1;
+    uint32_t m = 1, lg = 0;
+    while (m < n) {
+        m <<= 1;
+        ++lg;
+    }
     const uint32_t half = m >> 1;
-    for (uint32_t k = 2; k <= m; k <<= 1) {
-        // flip step: partner mirrored inside each block of k
-        for (uint32_t i = tid; i < half; i += nthreads) {
-            const uint32_t blk = i / (k >> 1), o = i % (k >> 1);
-            const uint32_t lo = blk * k + o, hi = blk * k + (k - 1 - o);
+    for (uint32_t lk = 1; lk <= lg; ++lk) {
+        const uint32_t k = 1u << lk;
+        for (uint32_t i = tid; i < half; i += nthreads) {  // flip step: partner mirrored inside each block of k
+            const uint32_t blk = i >> (lk - 1), o = i & ((k >> 1) - 1);
+            const uint32_t lo = (blk << lk) + o, hi = (blk << lk) + (k - 1 - o);
             if (hi < n) {
-                const unsigned long long a = s[lo], b = s[hi];
+                const u64 a = s[lo], b = s[hi];
                 if (a > b) {
                     s[lo] = b;
                     s[hi] = a;
@@ -121,7 +146,7 @@ __device__ __forceinline__ void bitonic_sort_ascending(KeyPtr s, uint32_t n, int
             for (uint32_t i = tid; i < half; i += nthreads) {
                 const uint32_t lo = ((i & ~(j - 1)) << 1) | (i & (j - 1)), hi = lo + j;
                 if (hi < n) {
-                    const unsigned long long a = s[lo], b = s[hi];
+                    const u64 a = s[lo], b = s[hi];
                     if (a > b) {
                         s[lo] = b;
                         s[hi] = a;
@@ -133,8 +158,122 @@ __device__ __forceinline__ void bitonic_sort_ascending(KeyPtr s, uint32_t n, int
     }
 }
 
+// ---- linear-bucket sort of one tile segment held in shared memory ------------------------------------------
+// s_in[n] unsorted keys -> s_out[n] sorted.  PER = ceil(CAP / THREADS) keys per thread.
+template <int THREADS, int PER, int MAXB>
+__device__ __forceinline__ void bucket_sort(const u64* __restrict__ gkeys, uint32_t n, u64* s_in, u64* s_out,
+                                            uint32_t* s_cnt, uint32_t* s_red) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = THREADS / 32;
+    // load + depth range
+    uint32_t dmin = 0xffffffffu, dmax = 0u;
+    u64 mine[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const uint32_t i = tid + k * THREADS;
+        if (i < n) {
+            mine[k] = gkeys[i];
+            const uint32_t d = (uint32_t)(mine[k] >> 32);
+            dmin = min(dmin, d);
+            dmax = max(dmax, d);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        dmin = min(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+        dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    }
+    if (lane == 0) {
+        s_red[wid] = dmin;
+        s_red[NW + wid] = dmax;
+    }
+    uint32_t nb = 1;
+    while (nb < n && nb < (uint32_t)MAXB) nb <<= 1;
+    for (uint32_t i = tid; i < nb; i += THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    dmin = s_red[0];
+    dmax = s_red[NW];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) {
+        dmin = min(dmin, s_red[w]);
+        dmax = max(dmax, s_red[NW + w]);
+    }
+    // monotone map depth bits -> bucket (uint->float, * positive constant, truncation are all monotone)
+    const float scale = (float)nb / ((float)(dmax - dmin) + 1.0f);
+    uint32_t br[PER];  // bucket | rank<<16
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const uint32_t i = tid + k * THREADS;
+        if (i < n) {
+            const uint32_t d = (uint32_t)(mine[k] >> 32);
+            const uint32_t b = min(nb - 1, (uint32_t)((float)(d - dmin) * scale));
+            const uint32_t r = atomicAdd(&s_cnt[b], 1u);
+            br[k] = b | (r << 16);
+        }
+    }
+    __syncthreads();
+    // exclusive scan of s_cnt[0..nb) in place, tracking the largest bucket
+    const uint32_t per = (nb + THREADS - 1) / THREADS;
+    const uint32_t b0 = min(nb, tid * per), b1 = min(nb, b0 + per);
+    uint32_t sum = 0, big = 0;
+    for (uint32_t b = b0; b < b1; ++b) {
+        sum += s_cnt[b];
+        big = max(big, s_cnt[b]);
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) big = max(big, __shfl_xor_sync(0xffffffffu, big, o));
+    __syncthreads();  // all reads of s_red above are done
+    if (lane == 31) s_red[wid] = incl;
+    if (lane == 0) s_red[NW + wid] = big;
+    __syncthreads();
+    uint32_t woff = 0, maxb = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        if (w < wid) woff += s_red[w];
+        maxb = max(maxb, s_red[NW + w]);
+    }
+    uint32_t off = woff + (incl - sum);
+    for (uint32_t b = b0; b < b1; ++b) {
+        const uint32_t c = s_cnt[b];
+        s_cnt[b] = off;
+        off += c;
+    }
+    if (tid == THREADS - 1) s_cnt[nb] = n;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const uint32_t i = tid + k * THREADS;
+        if (i < n) s_out[s_cnt[br[k] & 0xffffu] + (br[k] >> 16)] = mine[k];
+    }
+    __syncthreads();
+    if (maxb <= 48) {
+        for (uint32_t b = tid; b < nb; b += THREADS) {  // insertion sort inside each (tiny) bucket
+            const uint32_t lo = s_cnt[b], hi = s_cnt[b + 1];
+            for (uint32_t i = lo + 1; i < hi; ++i) {
+                const u64 v = s_out[i];
+                uint32_t j = i;
+                while (j > lo && s_out[j - 1] > v) {
+                    s_out[j] = s_out[j - 1];
+                    --j;
+                }
+                s_out[j] = v;
+            }
+        }
+        __syncthreads();
+    } else {
+        bitonic_sort_ascending(s_out, n, tid, THREADS);  // skewed depth distribution: still exact, just slower
+    }
+    (void)s_in;
+}
+
 // write sorted ids and gather the splat records into sorted order (coalesced 16-byte stores)
-__device__ __forceinline__ void emit_sorted(const unsigned long long* keys, uint32_t n, uint32_t start,
+__device__ __forceinline__ void emit_sorted(const u64* keys, uint32_t n, uint32_t start,
                                             const float4* __restrict__ splat, uint32_t* __restrict__ point_list,
                                             float4* __restrict__ inst_splat, int tid, int nthreads) {
     for (uint32_t i = tid; i < n; i += nthreads) point_list[start + i] = (uint32_t)keys[i];
@@ -145,43 +284,53 @@ __device__ __forceinline__ void emit_sorted(const unsigned long long* keys, uint
     }
 }
 
-// ---- K4: one CTA per tile, segment <= FS_SORT_SMEM_CAP sorted in 32 KB of shared memory --------------------
+// ---- K4: one CTA per tile, segments of up to FS_SORT_SMEM_CAP keys -----------------------------------------
 constexpr int kSortThreads = 256;
+constexpr int kSortPer = FS_SORT_SMEM_CAP / kSortThreads;
 __global__ void __launch_bounds__(kSortThreads)
-tile_sort_kernel(const uint2* __restrict__ ranges, const unsigned long long* __restrict__ keys,
-                 const float4* __restrict__ splat, uint32_t* __restrict__ point_list, float4* __restrict__ inst_splat,
-                 uint32_t Rcap) {
-    __shared__ unsigned long long s_keys[FS_SORT_SMEM_CAP];
+tile_sort_kernel(const uint2* __restrict__ ranges, const u64* __restrict__ keys, const float4* __restrict__ splat,
+                 uint32_t* __restrict__ point_list, float4* __restrict__ inst_splat, uint32_t Rcap) {
+    __shared__ u64 s_out[FS_SORT_SMEM_CAP];
+    __shared__ uint32_t s_cnt[FS_SORT_SMEM_CAP + 1];
+    __shared__ uint32_t s_red[2 * (kSortThreads / 32)];
     const uint2 r = ranges[blockIdx.x];
     const uint32_t n = r.y - r.x;
     if (n == 0 || n > FS_SORT_SMEM_CAP || r.y > Rcap) return;
-    for (uint32_t i = threadIdx.x; i < n; i += kSortThreads) s_keys[i] = keys[r.x + i];
-    __syncthreads();
-    bitonic_sort_ascending(s_keys, n, threadIdx.x, kSortThreads);
-    emit_sorted(s_keys, n, r.x, splat, point_list, inst_splat, threadIdx.x, kSortThreads);
+    bucket_sort<kSortThreads, kSortPer, FS_SORT_SMEM_CAP>(keys + r.x, n, nullptr, s_out, s_cnt, s_red);
+    emit_sorted(s_out, n, r.x, splat, point_list, inst_splat, threadIdx.x, kSortThreads);
 }
 
 // ---- K4b: persistent CTAs over the (usually empty) list of oversized tiles ---------------------------------
-// up to kBigSmemCap instances in dynamic shared memory; beyond that, the same network in global memory.
+// n <= kBigBucketCap: bucket sort in dynamic shared memory; n <= kBigSmemCap: bitonic in shared memory;
+// beyond: the same network directly on the global key segment.
 constexpr int kBigThreads = 1024;
+constexpr uint32_t kBigBucketCap = 8192;
 constexpr uint32_t kBigSmemCap = 24576;  // 192 KB of 64-bit keys
+constexpr size_t kBigSmemBytes = kBigSmemCap * sizeof(u64);
 __global__ void __launch_bounds__(kBigThreads)
 big_tile_sort_kernel(const uint32_t* __restrict__ big_tiles, const uint2* __restrict__ ranges,
-                     unsigned long long* __restrict__ keys, const float4* __restrict__ splat,
-                     uint32_t* __restrict__ point_list, float4* __restrict__ inst_splat, uint32_t Rcap) {
-    extern __shared__ __align__(16) unsigned long long d_keys[];
+                     u64* __restrict__ keys, const float4* __restrict__ splat, uint32_t* __restrict__ point_list,
+                     float4* __restrict__ inst_splat, uint32_t Rcap) {
+    extern __shared__ __align__(16) u64 d_smem[];
+    __shared__ uint32_t s_red[2 * (kBigThreads / 32)];
     const uint32_t nbig = big_tiles[0];
     for (uint32_t b = blockIdx.x; b < nbig; b += gridDim.x) {
         const uint2 r = ranges[big_tiles[1 + b]];
         const uint32_t n = r.y - r.x;
         if (r.y > Rcap) continue;
-        if (n <= kBigSmemCap) {
-            for (uint32_t i = threadIdx.x; i < n; i += kBigThreads) d_keys[i] = keys[r.x + i];
+        if (n <= kBigBucketCap) {
+            u64* s_out = d_smem;                                                  // 64 KB
+            uint32_t* s_cnt = reinterpret_cast<uint32_t*>(d_smem + kBigBucketCap);  // 32 KB + 4
+            bucket_sort<kBigThreads, kBigBucketCap / kBigThreads, kBigBucketCap>(keys + r.x, n, nullptr, s_out, s_cnt,
+                                                                               s_red);
+            emit_sorted(s_out, n, r.x, splat, point_list, inst_splat, threadIdx.x, kBigThreads);
+        } else if (n <= kBigSmemCap) {
+            for (uint32_t i = threadIdx.x; i < n; i += kBigThreads) d_smem[i] = keys[r.x + i];
             __syncthreads();
-            bitonic_sort_ascending(d_keys, n, threadIdx.x, kBigThreads);
-            emit_sorted(d_keys, n, r.x, splat, point_list, inst_splat, threadIdx.x, kBigThreads);
+            bitonic_sort_ascending(d_smem, n, threadIdx.x, kBigThreads);
+            emit_sorted(d_smem, n, r.x, splat, point_list, inst_splat, threadIdx.x, kBigThreads);
         } else {
-            unsigned long long* g = keys + r.x;
+            u64* g = keys + r.x;
             bitonic_sort_ascending(g, n, threadIdx.x, kBigThreads);
             emit_sorted(g, n, r.x, splat, point_list, inst_splat, threadIdx.x, kBigThreads);
         }
@@ -199,23 +348,35 @@ void fs_launch_binning(int P, int W, int H, char* ws, const fs_workspace_layout&
     auto* tile_cursor = reinterpret_cast<uint32_t*>(ws + L.tile_cursor);
     auto* ranges = reinterpret_cast<uint2*>(ws + L.ranges);
     auto* big = reinterpret_cast<uint32_t*>(ws + L.big_tiles);
-    auto* keys = reinterpret_cast<unsigned long long*>(ws + L.inst_keys);
+    auto* work_order = reinterpret_cast<uint32_t*>(ws + L.work_order);
+    auto* keys = reinterpret_cast<u64*>(ws + L.inst_keys);
     auto* splat = reinterpret_cast<const float4*>(ws + L.splat);
     auto* point_list = reinterpret_cast<uint32_t*>(ws + L.point_list);
     auto* inst_splat = reinterpret_cast<float4*>(ws + L.inst_splat);
-
-    tile_scan_kernel<<<1, kScanThreads, 0, stream>>>(Tn, tile_count, tile_cursor, ranges, big, info, Rcap);
-    scatter_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, gx, reinterpret_cast<const ushort4*>(ws + L.rect),
-                                                        reinterpret_cast<const float*>(ws + L.depths), tile_cursor,
-                                                        keys, Rcap);
-    tile_sort_kernel<<<Tn, kSortThreads, 0, stream>>>(ranges, keys, splat, point_list, inst_splat, Rcap);
+    {
+        FsStageTimer t(FS_STAGE_TILE_SCAN, stream);
+        tile_scan_kernel<<<1, kScanThreads, 0, stream>>>(Tn, tile_count, tile_cursor, ranges, big, work_order, info,
+                                                         Rcap);
+    }
+    {
+        FsStageTimer t(FS_STAGE_SCATTER, stream);
+        scatter_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, gx, reinterpret_cast<const ushort4*>(ws + L.rect),
+                                                            reinterpret_cast<const float*>(ws + L.depths),
+                                                            tile_cursor, keys, Rcap);
+    }
+    {
+        FsStageTimer t(FS_STAGE_TILE_SORT, stream);
+        tile_sort_kernel<<<Tn, kSortThreads, 0, stream>>>(ranges, keys, splat, point_list, inst_splat, Rcap);
+    }
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(big_tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(kBigSmemCap * sizeof(unsigned long long)));
+        cudaFuncSetAttribute(big_tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBigSmemBytes);
         attr_set = true;
     }
-    big_tile_sort_kernel<<<64, kBigThreads, kBigSmemCap * sizeof(unsigned long long), stream>>>(
-        big, ranges, keys, splat, point_list, inst_splat, Rcap);
+    {
+        FsStageTimer t(FS_STAGE_BIG_TILE_SORT, stream);
+        big_tile_sort_kernel<<<64, kBigThreads, kBigSmemBytes, stream>>>(big, ranges, keys, splat, point_list,
+                                                                        inst_splat, Rcap);
+    }
     fs_count_launch(4);
 }

@@ -1,4 +1,4 @@
-// Front-to-back alpha blend of one 16x16 tile per CTA.
+// Front-to-back alpha blend.
 //
 // Replaces DGR cuda_rasterizer/forward.cu:261-374 (renderCUDA).  Same per-pixel rule, evaluated in the same
 // fp32 operation order, so final_T / n_contrib / colour agree with the reference:
@@ -7,75 +7,98 @@
 //     stop the pixel when T (1 - alpha) < 1e-4 ; else C += rgb * alpha * T, T *= 1 - alpha
 //
 // B200 design:
-//   * the tile's splat records were gathered into depth order by the sort kernel, so a batch of 256 records
-//     is one contiguous 12 KB block: it is staged with ONE cp.async.bulk (TMA 1-D, UBLKCP) per batch into a
-//     2-stage shared-memory ring guarded by mbarriers -- no per-thread gather loads, no index indirection;
-//   * each warp owns an 8x4 pixel block.  Per 32 records, every lane tests one record's conservative
-//     alpha>=1/255 bounding box against the warp's block and the warp walks only the ballot survivors.
-//     Skipped records could not have contributed to any of the warp's pixels, and positions in the list are
-//     still counted, so n_contrib is unchanged.  This removes ~75-85 % of the exp/FMA work of the reference's
-//     every-pixel-visits-every-record loop, which is what bounds this kernel (it is SFU/issue bound, not HBM
-//     bound: algorithmic traffic is 48*R + 20*W*H + 8*Tn bytes).
+//   * work unit = one 8x4 pixel block of one tile, owned by ONE WARP.  Units are handed out heaviest-first
+//     from a device work list (built by the tile scan) through an atomic counter to persistent warps, so the
+//     few hundred dense tiles of a head spread evenly over all 592 SM sub-partitions instead of following
+//     the launch order (a CTA-per-tile grid left the busiest sub-partition with 2.4x the average work);
+//   * the tile's splat records were gathered into depth order by the sort kernel, so a batch of records is
+//     one contiguous block: each warp streams it with cp.async.bulk (TMA 1-D, UBLKCP) into its private
+//     2-stage shared-memory ring guarded by mbarriers -- no per-thread gather loads, no index indirection,
+//     no CTA-wide barrier;
+//   * per 32 records, every lane tests one record's conservative alpha>=1/255 bounding box against the
+//     warp's block and the warp walks only the ballot survivors, four at a time so that the four
+//     power/exp chains overlap.  Skipped records could not have contributed to any of the warp's pixels, and
+//     positions in the list are still counted, so n_contrib is unchanged.
+// The kernel is issue/SFU bound, not HBM bound: algorithmic traffic is 48*R + 20*W*H + 8*Tn bytes.
 #include "common.cuh"
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kBatch = 256;
+constexpr int kWarps = 8;     // warps per CTA (independent; they only share the CTA's shared memory)
+constexpr int kBatch = 64;    // records per stage
 constexpr int kStages = 2;
+constexpr int kGroup = 4;
 
-__global__ void __launch_bounds__(kThreads)
-blend_forward_kernel(const uint2* __restrict__ ranges, const SplatRec* __restrict__ inst_splat, int W, int H,
+struct WarpStage {
+    SplatRec rec[kStages][kBatch];
+};
+
+__global__ void __launch_bounds__(kWarps * 32)
+blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ work_order, int n_tiles,
+                     uint32_t* __restrict__ work_counter, const SplatRec* __restrict__ inst_splat, int W, int H,
                      const float* __restrict__ bg_color, float* __restrict__ out_color, float* __restrict__ final_T,
                      uint32_t* __restrict__ n_contrib, uint32_t Rcap) {
-    __shared__ __align__(128) SplatRec s_rec[kStages][kBatch];
-    __shared__ __align__(8) uint64_t s_full[kStages];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    WarpStage* stages = reinterpret_cast<WarpStage*>(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sizeof(WarpStage) * kWarps);
 
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int gx = (W + FS_TILE - 1) / FS_TILE;
-    const int tile = blockIdx.x;
-    const int tile_x = tile % gx, tile_y = tile / gx;
-    // warp -> 8x4 pixel block, lane -> pixel
-    const int bx = tile_x * FS_TILE + (wid & 1) * 8, by = tile_y * FS_TILE + (wid >> 1) * 4;
-    const int px = bx + (lane & 7), py = by + (lane >> 3);
-    const bool inside = px < W && py < H;
-    const float pxf = (float)px, pyf = (float)py;
-    // warp block bounds in pixel-centre coordinates
-    const float wx0 = (float)bx, wx1 = (float)min(bx + 7, W - 1), wy0 = (float)by, wy1 = (float)min(by + 3, H - 1);
-
-    uint2 range = ranges[tile];
-    if (range.y > Rcap) range = make_uint2(0u, 0u);  // overflowed frame: flagged in the header, stay in bounds
-    const uint32_t total = range.y - range.x;
-    const int nbatches = (int)((total + kBatch - 1) / kBatch);
-
-    if (tid == 0) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    SplatRec(*rec_ring)[kBatch] = stages[wid].rec;
+    uint64_t* s_full = bars + wid * kStages;
+    if (lane == 0) {
         fs::mbar_init(&s_full[0], 1);
         fs::mbar_init(&s_full[1], 1);
         fs::mbar_fence_init();
     }
-    __syncthreads();
+    __syncwarp();
+    uint32_t fills = 0;  // batches issued so far by this warp: stage = fills & 1, parity = (fills >> 1) & 1
 
-    auto issue = [&](int b) {
-        const uint32_t cnt = min((uint32_t)kBatch, total - (uint32_t)b * kBatch);
-        const uint32_t bytes = cnt * (uint32_t)sizeof(SplatRec);
-        fs::mbar_expect_tx(&s_full[b & 1], bytes);
-        fs::bulk_g2s(&s_rec[b & 1][0], inst_splat + range.x + (size_t)b * kBatch, bytes, &s_full[b & 1]);
-    };
-    if (tid == 0 && nbatches > 0) issue(0);
+    const int gx = (W + FS_TILE - 1) / FS_TILE;
+    const float bg0 = __ldg(bg_color + 0), bg1 = __ldg(bg_color + 1), bg2 = __ldg(bg_color + 2);
+    const uint32_t n_units = (uint32_t)n_tiles * 8u;
 
-    float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f;
-    uint32_t last_contributor = 0;
-    bool done = !inside;
-    bool warp_done = __all_sync(0xffffffffu, done);
+    for (;;) {
+        uint32_t unit = 0;
+        if (lane == 0) unit = atomicAdd(work_counter, 1u);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= n_units) break;
+        const int tile = (int)work_order[unit >> 3];
+        const int blk = (int)(unit & 7u);  // 8x4 block inside the tile: 2 columns x 4 rows
+        const int tile_x = tile % gx, tile_y = tile / gx;
+        const int bx = tile_x * FS_TILE + (blk & 1) * 8, by = tile_y * FS_TILE + (blk >> 1) * 4;
+        const int px = bx + (lane & 7), py = by + (lane >> 3);
+        const bool inside = px < W && py < H;
+        const float pxf = (float)px, pyf = (float)py;
+        const float wx0 = (float)bx, wx1 = (float)min(bx + 7, W - 1), wy0 = (float)by, wy1 = (float)min(by + 3, H - 1);
 
-    int b = 0;
-    for (; b < nbatches; ++b) {
-        if (tid == 0 && b + 1 < nbatches) issue(b + 1);  // stage (b+1)&1 was released by the barrier below
-        fs::mbar_wait(&s_full[b & 1], (uint32_t)(b >> 1) & 1u);
-        const SplatRec* rec = s_rec[b & 1];
-        const int cnt = (int)min((uint32_t)kBatch, total - (uint32_t)b * kBatch);
-        if (!warp_done) {
-            for (int c = 0; c < cnt; c += 32) {
+        uint2 range = ranges[tile];
+        if (range.y > Rcap) range = make_uint2(0u, 0u);  // overflowed frame: flagged in the header, stay in bounds
+        const uint32_t total = range.y - range.x;
+        const int nbatches = (int)((total + kBatch - 1) / kBatch);
+
+        auto issue = [&](int b) {  // lane 0 only
+            const uint32_t cnt = min((uint32_t)kBatch, total - (uint32_t)b * kBatch);
+            const uint32_t bytes = cnt * (uint32_t)sizeof(SplatRec);
+            const uint32_t s = (fills + (uint32_t)b) & 1u;
+            fs::mbar_expect_tx(&s_full[s], bytes);
+            fs::bulk_g2s(&rec_ring[s][0], inst_splat + range.x + (size_t)b * kBatch, bytes, &s_full[s]);
+        };
+        if (lane == 0 && nbatches > 0) issue(0);
+
+        float T = 1.0f, C0 = 0.0f, C1 = 0.0f, C2 = 0.0f;
+        uint32_t last_contributor = 0;
+        bool done = !inside;
+        bool warp_done = __all_sync(0xffffffffu, done);
+
+        int b = 0;
+        for (; b < nbatches; ++b) {
+            __syncwarp();  // every lane is done reading the stage that batch b+1 will overwrite
+            if (lane == 0 && b + 1 < nbatches) issue(b + 1);
+            const uint32_t f = fills + (uint32_t)b;
+            fs::mbar_wait(&s_full[f & 1u], (f >> 1) & 1u);
+            const SplatRec* rec = rec_ring[f & 1u];
+            const int cnt = (int)min((uint32_t)kBatch, total - (uint32_t)b * kBatch);
+            for (int c = 0; c < cnt && !warp_done; c += 32) {
                 const int j = c + lane;
                 bool hit = false;
                 if (j < cnt) {
@@ -84,55 +107,91 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const SplatRec* __restric
                           !(q0.x + q0.z < wx0 || q0.x - q0.z > wx1 || q0.y + q0.w < wy0 || q0.y - q0.w > wy1);
                 }
                 unsigned m = __ballot_sync(0xffffffffu, hit);
+                // Walk the survivors four at a time: the four power/exp chains are independent and overlap;
+                // only the short transmittance update below is sequential (front-to-back order preserved).
                 while (m) {
-                    const int bit = __ffs(m) - 1;
-                    m &= m - 1;
-                    if (!done) {
-                        const float4 q0 = rec[c + bit].q0;
-                        const float4 q1 = rec[c + bit].q1;
-                        const float dx = fs::sub(q0.x, pxf), dy = fs::sub(q0.y, pyf);
-                        const float power = fs::splat_power(dx, dy, q1.x, q1.y, q1.z);
-                        if (power <= 0.0f) {
-                            const float alpha = fminf(0.99f, fs::mul(q1.w, expf(power)));
-                            if (alpha >= 1.0f / 255.0f) {
-                                const float test_T = fs::mul(T, fs::sub(1.0f, alpha));
-                                if (test_T < 0.0001f) {
-                                    done = true;
-                                } else {
-                                    const float4 q2 = rec[c + bit].q2;
-                                    C0 = fs::mad(T, fs::mul(alpha, q2.x), C0);
-                                    C1 = fs::mad(T, fs::mul(alpha, q2.y), C1);
-                                    C2 = fs::mad(T, fs::mul(alpha, q2.z), C2);
-                                    T = test_T;
-                                    last_contributor = (uint32_t)b * kBatch + (uint32_t)(c + bit) + 1u;
-                                }
-                            }
-                        }
+                    int jj[kGroup];
+                    bool live[kGroup];
+                    float alpha[kGroup];
+                    float4 col[kGroup];
+#pragma unroll
+                    for (int k = 0; k < kGroup; ++k) {  // branch-free extraction of the next four set bits
+                        const int fbit = __ffs(m);
+                        live[k] = fbit != 0;
+                        jj[k] = live[k] ? c + fbit - 1 : c;
+                        m &= m - 1;
+                    }
+                    // stage-wise formulation: each statement group is independent across k, so the four chains
+                    // issue interleaved instead of back to back
+                    float4 q0[kGroup], q1[kGroup];
+#pragma unroll
+                    for (int k = 0; k < kGroup; ++k) {
+                        q0[k] = rec[jj[k]].q0;
+                        q1[k] = rec[jj[k]].q1;
+                        col[k] = rec[jj[k]].q2;
+                    }
+                    float power[kGroup];
+#pragma unroll
+                    for (int k = 0; k < kGroup; ++k) {
+                        const float dx = fs::sub(q0[k].x, pxf), dy = fs::sub(q0[k].y, pyf);
+                        power[k] = fs::splat_power(dx, dy, q1[k].x, q1[k].y, q1[k].z);
+                    }
+                    float ex[kGroup];
+#pragma unroll
+                    for (int k = 0; k < kGroup; ++k) ex[k] = expf(power[k]);
+#pragma unroll
+                    for (int k = 0; k < kGroup; ++k) {
+                        const float a = fminf(0.99f, fs::mul(q1[k].w, ex[k]));
+                        // alpha < 0 marks "skip": not a survivor, power > 0, or alpha < 1/255
+                        alpha[k] = (live[k] && power[k] <= 0.0f && a >= 1.0f / 255.0f) ? a : -1.0f;
+                    }
+                    // The vote ends the basic block: all four alphas are needed here, so the scheduler overlaps
+                    // the four chains instead of trailing them behind the transmittance chain below.  It also
+                    // skips the update when no pixel of the block is touched by this group.
+                    if (!__any_sync(0xffffffffu, (alpha[0] >= 0.0f) | (alpha[1] >= 0.0f) | (alpha[2] >= 0.0f) |
+                                                     (alpha[3] >= 0.0f)))
+                        continue;
+#pragma unroll
+                    for (int k = 0; k < kGroup; ++k) {  // sequential transmittance update, predicated (no branches)
+                        const float test_T = fs::mul(T, fs::sub(1.0f, alpha[k]));
+                        const bool act = alpha[k] >= 0.0f && !done;
+                        const bool stop = act && test_T < 0.0001f;
+                        const bool apply = act && !stop;
+                        done = done || stop;
+                        const float n0 = fs::mad(T, fs::mul(alpha[k], col[k].x), C0);
+                        const float n1 = fs::mad(T, fs::mul(alpha[k], col[k].y), C1);
+                        const float n2 = fs::mad(T, fs::mul(alpha[k], col[k].z), C2);
+                        C0 = apply ? n0 : C0;
+                        C1 = apply ? n1 : C1;
+                        C2 = apply ? n2 : C2;
+                        T = apply ? test_T : T;
+                        last_contributor = apply ? (uint32_t)b * kBatch + (uint32_t)jj[k] + 1u : last_contributor;
                     }
                 }
-                if (__all_sync(0xffffffffu, done)) {
-                    warp_done = true;
-                    break;
-                }
+                warp_done = __all_sync(0xffffffffu, done);
+            }
+            if (warp_done) {  // every pixel of the block has terminated: stop streaming
+                ++b;
+                break;
             }
         }
-        // all warps finished with this stage (it may be refilled next iteration); stop when every pixel is done
-        if (__syncthreads_and(warp_done)) {
+        // a prefetch issued for batch `b` may still be in flight: drain it so the ring can be reused
+        if (b < nbatches && b > 0) {
+            const uint32_t f = fills + (uint32_t)b;
+            fs::mbar_wait(&s_full[f & 1u], (f >> 1) & 1u);
             ++b;
-            break;
         }
-    }
-    // a prefetch issued for batch `b` may still be in flight: drain it before the CTA retires
-    if (b < nbatches && b > 0) fs::mbar_wait(&s_full[b & 1], (uint32_t)(b >> 1) & 1u);
+        fills += (uint32_t)b;  // number of batches actually issued for this unit
 
-    if (inside) {
-        const size_t pid = (size_t)py * W + px;
-        final_T[pid] = T;
-        n_contrib[pid] = last_contributor;
-        const size_t plane = (size_t)H * W;
-        out_color[pid] = fs::mad(__ldg(bg_color + 0), T, C0);
-        out_color[plane + pid] = fs::mad(__ldg(bg_color + 1), T, C1);
-        out_color[2 * plane + pid] = fs::mad(__ldg(bg_color + 2), T, C2);
+        if (inside) {
+            const size_t pid = (size_t)py * W + px;
+            final_T[pid] = T;
+            n_contrib[pid] = last_contributor;
+            const size_t plane = (size_t)H * W;
+            out_color[pid] = fs::mad(bg0, T, C0);
+            out_color[plane + pid] = fs::mad(bg1, T, C1);
+            out_color[2 * plane + pid] = fs::mad(bg2, T, C2);
+        }
     }
 }
 
@@ -141,9 +200,20 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const SplatRec* __restric
 void fs_launch_blend_forward(int W, int H, const float* bg, float* out_color, char* ws, const fs_workspace_layout& L,
                              cudaStream_t stream) {
     const int gx = (W + FS_TILE - 1) / FS_TILE, gy = (H + FS_TILE - 1) / FS_TILE;
-    blend_forward_kernel<<<gx * gy, kThreads, 0, stream>>>(
-        reinterpret_cast<const uint2*>(ws + L.ranges), reinterpret_cast<const SplatRec*>(ws + L.inst_splat), W, H, bg,
-        out_color, reinterpret_cast<float*>(ws + L.final_T), reinterpret_cast<uint32_t*>(ws + L.n_contrib),
+    FsStageTimer timer(FS_STAGE_BLEND_FWD, stream);
+    const size_t smem = sizeof(WarpStage) * kWarps + sizeof(uint64_t) * kStages * kWarps;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(blend_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    auto* info = reinterpret_cast<fs_frame_info*>(ws + L.info);
+    const int ctas_per_sm = fs_tuning("FATESPLAT_FWD_CTAS_PER_SM", 1);
+    const int grid = min(fs_num_sms() * ctas_per_sm, (gx * gy * 8 + kWarps - 1) / kWarps);
+    blend_forward_kernel<<<grid, kWarps * 32, smem, stream>>>(
+        reinterpret_cast<const uint2*>(ws + L.ranges), reinterpret_cast<const uint32_t*>(ws + L.work_order), gx * gy,
+        &info->reserved[1], reinterpret_cast<const SplatRec*>(ws + L.inst_splat), W, H, bg, out_color,
+        reinterpret_cast<float*>(ws + L.final_T), reinterpret_cast<uint32_t*>(ws + L.n_contrib),
         (uint32_t)L.instance_capacity);
     fs_count_launch(1);
 }

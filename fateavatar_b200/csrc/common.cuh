@@ -20,7 +20,7 @@ static_assert(sizeof(SplatRec) == 48, "splat record is 48 bytes");
 namespace fs {
 
 // ---- exact-sequence fp32 helpers (never contracted or re-associated by nvcc) --------------------------
-// The op order mirrors the sm_100 SASS of the reference build; see oracle/splat_oracle.c header.
+// The op order mirrors the sm_100 SASS of the reference build ("Arithmetic contract").
 __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
@@ -159,5 +159,29 @@ struct FsLayout : fs_workspace_layout {};
 void fs_compute_layout(int P, int W, int H, size_t Rcap, fs_workspace_layout* L);
 void fs_set_error(const char* fmt, ...);
 void fs_count_launch(int n);
+int fs_num_sms();
+int fs_tuning(const char* env_name, int default_value);  // integer tuning knob, read once from the environment
 
-#define FS_SORT_SMEM_CAP 4096  // instances a tile may hold to be sorted in shared memory by the small kernel
+// Optional per-stage timing (fs_profile_enable): CUDA events recorded on the launching stream around a stage.
+enum FsStage {
+    FS_STAGE_PREPROCESS = 0,
+    FS_STAGE_TILE_SCAN,
+    FS_STAGE_SCATTER,
+    FS_STAGE_TILE_SORT,
+    FS_STAGE_BIG_TILE_SORT,
+    FS_STAGE_BLEND_FWD,
+    FS_STAGE_BLEND_BWD,
+    FS_STAGE_PREPROCESS_BWD,
+    FS_STAGE_KNN,
+    FS_STAGE_COUNT
+};
+struct FsStageTimer {  // RAII: records start in the ctor and stop in the dtor when profiling is on
+    FsStageTimer(int stage, cudaStream_t stream);
+    ~FsStageTimer();
+    int slot;
+    cudaStream_t stream;
+};
+
+#define FS_SORT_SMEM_CAP 2048  // instances a tile may hold to be sorted by the one-CTA-per-tile kernel
+// Per-tile counters live 128 bytes apart: L2 atomics to one line serialise, and only a few hundred tiles are hot.
+#define FS_CNT_STRIDE 32

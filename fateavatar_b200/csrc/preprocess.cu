@@ -80,7 +80,6 @@ preprocess_kernel(int P, int D, int M, const float* __restrict__ means3D, const 
     __shared__ __align__(16) float s_scale[kThreads * 3];
     __shared__ __align__(16) float s_sh[kThreads * 3];
     __shared__ float s_view[16], s_proj[16], s_cam[3];
-    __shared__ uint32_t s_visible;
 
     const int base = blockIdx.x * kThreads;
     const int idx = base + threadIdx.x;
@@ -89,7 +88,6 @@ preprocess_kernel(int P, int D, int M, const float* __restrict__ means3D, const 
         s_proj[threadIdx.x] = projmatrix[threadIdx.x];
     }
     if (threadIdx.x < 3) s_cam[threadIdx.x] = cam_pos[threadIdx.x];
-    if (threadIdx.x == 0) s_visible = 0;
     stage3(means3D, s_xyz, base, P);
     if (cov3D_precomp == nullptr) stage3(scales, s_scale, base, P);
     const bool sh_staged = (colors_precomp == nullptr) && (M == 1);
@@ -190,7 +188,7 @@ preprocess_kernel(int P, int D, int M, const float* __restrict__ means3D, const 
                     splat[idx] = rec;
                     clamped[idx] = cl;
                     for (int y = y0; y < y1; ++y)
-                        for (int x = x0; x < x1; ++x) atomicAdd(&tile_count[y * gx + x], 1u);
+                        for (int x = x0; x < x1; ++x) atomicAdd(&tile_count[(size_t)(y * gx + x) * FS_CNT_STRIDE], 1u);
                 }
             }
         } else if (prefiltered) {
@@ -200,9 +198,8 @@ preprocess_kernel(int P, int D, int M, const float* __restrict__ means3D, const 
         tiles_touched[idx] = ntiles;
         rect[idx] = rc;
     }
-    const uint32_t nvis = __syncthreads_count(visible);
-    if (threadIdx.x == 0 && nvis) atomicAdd(&info->num_visible, nvis);
-    (void)s_visible;
+    const unsigned vmask = __ballot_sync(0xffffffffu, visible);
+    if ((threadIdx.x & 31) == 0 && vmask) atomicAdd(&info->num_visible, (uint32_t)__popc(vmask));
 }
 
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ viewmatrix,
@@ -222,6 +219,7 @@ void fs_launch_preprocess(int P, int D, int M, const float* means3D, const float
                           int prefiltered, int* radii, char* ws, const fs_workspace_layout& L, cudaStream_t stream) {
     const float focal_y = H / (2.0f * tan_fovy);
     const float focal_x = W / (2.0f * tan_fovx);
+    FsStageTimer timer(FS_STAGE_PREPROCESS, stream);
     preprocess_kernel<<<(P + kThreads - 1) / kThreads, kThreads, 0, stream>>>(
         P, D, M, means3D, scales, scale_modifier, rotations, opacities, shs, cov3D_precomp, colors_precomp, viewmatrix,
         projmatrix, cam_pos, W, H, tan_fovx, tan_fovy, focal_x, focal_y, prefiltered, radii,

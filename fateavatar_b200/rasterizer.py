@@ -134,7 +134,7 @@ def forward_raw(raster_settings, means3D, sh, colors_precomp, opacities, scales,
     rs = raster_settings
     P = means3D.shape[0]
     H, W = int(rs.image_height), int(rs.image_width)
-    m3 = _prep(means3D, "means3D", dev)
+    m3 = _prep(means3D, "means3D", dev) if P else means3D.contiguous()
     sh_c = _prep(sh, "sh", dev)
     cp_c = _prep(colors_precomp, "colors_precomp", dev)
     op_c = _prep(opacities, "opacities", dev)
@@ -336,6 +336,7 @@ def decode_workspace(workspace, P, W, H, capacity, num_rendered=None):
 
     info = view(L.info, 32, torch.int32, (8,))
     R = int(info[0].item()) if num_rendered is None or num_rendered < 0 else int(num_rendered)
+    R = min(R, int(capacity))  # an overflowed frame holds at most `capacity` instances
     splat = view(L.splat, P * 48, torch.float32, (P, 12))
     out = dict(
         num_rendered=R, info=info,
@@ -345,7 +346,7 @@ def decode_workspace(workspace, P, W, H, capacity, num_rendered=None):
         clamped=view(L.clamped, P * 4, torch.uint8, (P, 4))[:, :3],
         rect=view(L.rect, P * 8, torch.int16, (P, 4)),
         tiles_touched=view(L.tiles_touched, P * 4, torch.int32, (P,)),
-        tile_count=view(L.tile_count, Tn * 4, torch.int32, (Tn,)),
+        tile_count=view(L.tile_count, Tn * 128, torch.int32, (Tn, 32))[:, 0],  # counters are 128 B apart
         ranges=view(L.ranges, Tn * 8, torch.int32, (Tn, 2)),
         point_list=view(L.point_list, R * 4, torch.int32, (R,)),
         inst_splat=view(L.inst_splat, R * 48, torch.float32, (R, 12)),

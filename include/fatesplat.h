@@ -48,7 +48,7 @@ typedef struct fs_frame_info {
     uint32_t overflow;     /* 1 if R exceeded the workspace's instance capacity (frame is incomplete)       */
     uint32_t num_visible;  /* Gaussians with radii > 0                                                      */
     uint32_t max_tile_instances; /* heaviest tile's instance count                                         */
-    uint32_t reserved[4];
+    uint32_t reserved[4];  /* [0] prefiltered-violation flag, [1] forward work counter, [3] non-empty tiles */
 } fs_frame_info;
 
 /* Byte offsets (from the workspace base) of the named per-frame arrays: the parity taps.
@@ -66,12 +66,14 @@ typedef struct fs_workspace_layout {
     size_t tile_cursor;   /* uint32 [Tn]                                                     */
     size_t ranges;        /* uint32 [Tn][2]  (start,end) into point_list; (0,0) if empty     */
     size_t big_tiles;     /* uint32 [Tn+1]   [0]=count, then ids of tiles too large for the smem sort */
+    size_t work_order;    /* uint32 [Tn]     tile ids, heaviest first (work list of the blend kernels) */
     size_t inst_keys;     /* uint64 [Rcap]   (depth_bits<<32 | gaussian) per tile segment    */
     size_t inst_keys_alt; /* uint64 [Rcap]   ping-pong for the large-tile global sort        */
     size_t point_list;    /* uint32 [Rcap]   sorted Gaussian ids (== reference point_list)   */
     size_t inst_splat;    /* float4 [Rcap][3] splat records gathered in sorted order         */
     size_t final_T;       /* float  [H*W]                                                    */
     size_t n_contrib;     /* uint32 [H*W]                                                    */
+    size_t bwd_counter;   /* uint32 (256-byte slot) work counter of the backward blend, directly before grad_acc */
     size_t grad_acc;      /* float  [P][12]  backward accumulator: dmean2D.xy, dconic.xyw, dopacity, drgb, 3 pad */
     size_t instance_capacity; /* Rcap (count, not bytes)                                     */
 } fs_workspace_layout;
@@ -117,6 +119,16 @@ int fs_mark_visible(int P, const float* d_means3D, const float* d_viewmatrix, co
 size_t fs_knn_workspace_bytes(int P);
 int fs_knn_mean_dist2(int P, const float* d_points, float* d_mean_dist2, void* d_workspace, size_t workspace_bytes,
                       void* stream);
+
+/*
+ * Optional per-stage device timing for bench.py's roofline figures.  While enabled, every stage launch is
+ * bracketed by CUDA events on the launching stream; fs_profile_read waits for them and returns, per stage id
+ * (0 preprocess, 1 tile_scan, 2 scatter, 3 tile_sort, 4 big_tile_sort, 5 blend_forward, 6 blend_backward,
+ * 7 preprocess_backward, 8 knn), the summed milliseconds and the number of launches since the last read.
+ */
+#define FS_NUM_STAGES 9
+void fs_profile_enable(int on);
+int fs_profile_read(float* total_ms, int* counts, int n);
 
 /* Number of kernels the last fs_forward / fs_backward / fs_knn_mean_dist2 call on this thread launched. */
 int fs_last_launch_count(void);

@@ -1,0 +1,308 @@
+"""GPU parity tests (run with -m gpu on the B200): CUDA path vs the C oracle, vs the golden fixtures, and --
+when oracle/_ref was built -- vs the compiled reference itself, all through the C ABI.
+
+Bars (BASELINE.json north_star): tile/index outputs bit-exact; rendered colour within 1e-4 max abs (we
+assert 1e-5 vs the oracle, whose only arithmetic difference is glibc expf vs CUDA expf, and <= 1e-6 vs the
+compiled reference); gradients within 2e-4 of the tensor's max magnitude (sums of fp32 terms in a different
+order; the reference's own atomics are order-nondeterministic).
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from fateavatar_b200 import _lib, knn, rasterizer as R, render as rmod, scenes
+from oracle import oracle as orc
+from oracle import ref_loader
+from util import GRAD_NAMES, assert_grad_close, oracle_forward, settings
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def run_new(sc, dev, colors_precomp=None, cov3D_precomp=None, scale_modifier=1.0, dpix=None):
+    t = scenes.to_torch(sc, dev)
+    cam = t["camera"]
+    rs = settings(R, cam, t["bg"], sc["sh_degree"], scale_modifier)
+    cp = None if colors_precomp is None else torch.from_numpy(colors_precomp).to(dev)
+    c3 = None if cov3D_precomp is None else torch.from_numpy(cov3D_precomp).to(dev)
+    color, radii, st = R.forward_raw(rs, t["means3D"], None if cp is not None else t["shs"], cp, t["opacities"],
+                                     None if c3 is not None else t["scales"], None if c3 is not None else t["rotations"],
+                                     c3)
+    P = t["means3D"].shape[0]
+    taps = R.decode_workspace(st["workspace"], P, cam["W"], cam["H"], st["capacity"], st["num_rendered"]) if P else {}
+    grads = None
+    if dpix is not None:
+        grads = dict(zip(GRAD_NAMES, R.backward_raw(st, torch.from_numpy(dpix).to(dev))))
+    torch.cuda.synchronize()
+    return color, radii, st, taps, grads
+
+
+def check_forward_vs_oracle(color, radii, st, taps, o):
+    assert st["num_rendered"] == o["R"]
+    assert np.array_equal(radii.cpu().numpy(), o["radii"])
+    vis = o["radii"] > 0
+    assert np.array_equal(taps["tiles_touched"].cpu().numpy(), o["tiles_touched"].astype(np.int32))
+    assert np.array_equal(taps["ranges"].cpu().numpy(), o["ranges"].astype(np.int32))
+    assert np.array_equal(taps["point_list"].cpu().numpy(), o["point_list"].astype(np.int32))
+    for k in ("depths", "means2D", "conic_opacity", "rgb"):
+        got = taps[k].cpu().numpy()[vis]
+        assert np.array_equal(got.view(np.uint32), o[k][vis].view(np.uint32)), f"{k} not bit-exact"
+    assert np.array_equal(taps["clamped"].cpu().numpy()[vis], o["clamped"][vis])
+    nc = taps["n_contrib"].cpu().numpy()
+    assert (nc != o["n_contrib"].astype(np.int32)).mean() <= 1e-4
+    assert np.abs(taps["final_T"].cpu().numpy() - o["final_T"]).max() <= 1e-5
+    assert np.abs(color.cpu().numpy() - o["color"]).max() <= 1e-5  # north_star bar: 1e-4
+
+
+CASES = {
+    "config1_10k_256": lambda: scenes.config1_scene(),
+    "head_20k_300x200": lambda: scenes.head_scene(P=20000, W=300, H=200, scale_mult=3.0),
+    "ragged_image_37x50": lambda: scenes.config1_scene(P=700, W=50, H=37, seed=2),
+    "sh1": lambda: scenes.head_scene(P=3000, W=96, H=96, sh_degree=1, scale_mult=6.0, seed=4),
+    "sh2": lambda: scenes.head_scene(P=3000, W=96, H=96, sh_degree=2, scale_mult=6.0, seed=5),
+    "sh3": lambda: scenes.head_scene(P=3000, W=96, H=96, sh_degree=3, scale_mult=6.0, seed=6),
+    "single_gaussian": lambda: scenes.config1_scene(P=1, W=64, H=64, seed=9),
+    "p33": lambda: scenes.config1_scene(P=33, W=64, H=64, seed=10),
+    "large_tile_lists": lambda: scenes.head_scene(P=9000, W=64, H=64, scale_mult=10.0, seed=7),   # > 4096 per tile
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_forward_backward_vs_oracle(name, cuda_device):
+    sc = CASES[name]()
+    if name == "single_gaussian":
+        sc["means3D"][:] = 0.0
+    cam = sc["camera"]
+    dpix = np.random.default_rng(3).standard_normal((3, cam["H"], cam["W"])).astype(np.float32)
+    color, radii, st, taps, grads = run_new(sc, cuda_device, dpix=dpix)
+    o = oracle_forward(orc, sc)
+    check_forward_vs_oracle(color, radii, st, taps, o)
+    og = orc.backward(o, dpix)
+    for k in GRAD_NAMES:
+        assert_grad_close(k, grads[k].cpu().numpy(), og[k])
+
+
+def test_very_large_tile_list_global_sort_path(cuda_device):
+    """> 24576 instances in one tile: the sort falls back to global memory; results must not change."""
+    sc = scenes.head_scene(P=30000, W=32, H=32, scale_mult=30.0, seed=8)
+    color, radii, st, taps, _ = run_new(sc, cuda_device)
+    o = oracle_forward(orc, sc)
+    assert (o["ranges"][:, 1] - o["ranges"][:, 0]).max() > 24576
+    check_forward_vs_oracle(color, radii, st, taps, o)
+
+
+def test_colors_precomp_cov3d_precomp_scale_modifier_black_bg(cuda_device):
+    sc = scenes.head_scene(P=2500, W=80, H=64, scale_mult=6.0, seed=21)
+    sc["bg"] = np.zeros(3, np.float32)
+    rng = np.random.default_rng(0)
+    col = rng.uniform(0, 1, (2500, 3)).astype(np.float32)
+    dpix = rng.standard_normal((3, 64, 80)).astype(np.float32)
+    # precomputed colours (monogaussianavatar.py:411-421 variant)
+    color, radii, st, taps, grads = run_new(sc, cuda_device, colors_precomp=col, dpix=dpix)
+    o = oracle_forward(orc, sc, shs=None, colors_precomp=col)
+    assert np.abs(color.cpu().numpy() - o["color"]).max() <= 1e-5
+    og = orc.backward(o, dpix)
+    for k in ("dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dscales", "dL_drotations", "dL_dmeans2D"):
+        assert_grad_close(k, grads[k].cpu().numpy(), og[k])
+    # precomputed 3D covariance + scale modifier
+    o2 = oracle_forward(orc, sc, scale_modifier=1.7)
+    cov = o2["cov3D"].copy()
+    color2, radii2, st2, taps2, grads2 = run_new(sc, cuda_device, cov3D_precomp=cov, dpix=dpix)
+    o3 = oracle_forward(orc, sc, scales=None, rotations=None, cov3D_precomp=cov)
+    check_forward_vs_oracle(color2, radii2, st2, taps2, o3)
+    og3 = orc.backward(o3, dpix)
+    for k in ("dL_dcov3D", "dL_dmeans3D", "dL_dsh", "dL_dopacity"):
+        assert_grad_close(k, grads2[k].cpu().numpy(), og3[k])
+    color4, radii4, st4, taps4, _ = run_new(sc, cuda_device, scale_modifier=1.7)
+    check_forward_vs_oracle(color4, radii4, st4, taps4, o2)
+
+
+def test_empty_and_all_culled(cuda_device):
+    dev = cuda_device
+    sc = scenes.config1_scene(P=64, W=48, H=48)
+    t = scenes.to_torch(sc, dev)
+    rs = settings(R, t["camera"], t["bg"], 0)
+    z = lambda *s: torch.zeros(*s, device=dev)
+    color, radii, st = R.forward_raw(rs, z(0, 3), z(0, 1, 3), None, z(0, 1), z(0, 3), z(0, 4), None)
+    assert color.shape == (3, 48, 48) and float(color.abs().max()) == 0.0 and radii.numel() == 0  # reference: zeros
+    g = R.backward_raw(st, z(3, 48, 48))
+    assert all(x.shape[0] == 0 for x in g)
+    sc["means3D"] = sc["means3D"] + np.array([0, 0, 10], np.float32)  # behind the near plane
+    color, radii, st, taps, grads = run_new(sc, dev, dpix=np.ones((3, 48, 48), np.float32))
+    assert st["num_rendered"] == 0 and int(radii.abs().sum()) == 0
+    assert torch.allclose(color, torch.ones_like(color))
+    assert all(float(v.abs().max()) == 0.0 for v in grads.values())
+
+
+def test_capacity_overflow_is_retried_and_async_mode_detects_it(cuda_device, monkeypatch):
+    sc = scenes.head_scene(P=6000, W=128, H=128, scale_mult=8.0, seed=31)
+    o = oracle_forward(orc, sc)
+    monkeypatch.setattr(R, "_initial_capacity", lambda P, W, H, dev: 1024)  # far too small on purpose
+    color, radii, st, taps, _ = run_new(sc, cuda_device)
+    assert st["capacity"] >= o["R"] > 1024
+    check_forward_vs_oracle(color, radii, st, taps, o)
+    R.set_async(True)
+    try:
+        with pytest.raises(_lib.FateSplatError, match="overflowed"):
+            c, r, s = run_new(sc, cuda_device)[:3]
+            R.backward_raw(s, torch.zeros(3, 128, 128, device=cuda_device))
+        monkeypatch.undo()
+        color, radii, st, taps, _ = run_new(sc, cuda_device)  # capacity hint was raised: now fine, no host sync
+        st["num_rendered"] = o["R"]
+        taps = R.decode_workspace(st["workspace"], 6000, 128, 128, st["capacity"], o["R"])
+        check_forward_vs_oracle(color, radii, st, taps, o)
+    finally:
+        R.set_async(False)
+
+
+def test_autograd_through_render_mirror(cuda_device):
+    """The call FateAvatar makes: render(camera, gaussians, bg) -> loss.backward()."""
+    dev = cuda_device
+    sc = scenes.head_scene(P=3000, W=96, H=80, scale_mult=6.0, seed=41)
+    t = scenes.to_torch(sc, dev)
+    cam = t["camera"]
+    raw = dict(xyz=t["means3D"].clone().requires_grad_(True), feat=t["shs"].clone().requires_grad_(True),
+               scal=torch.log(t["scales"]).requires_grad_(True), rot=(t["rotations"] * 1.7).requires_grad_(True),
+               op=torch.logit(t["opacities"]).requires_grad_(True))
+    pc = rmod.SplatCloud(raw["xyz"], raw["feat"], raw["scal"], raw["rot"], raw["op"], 0)
+    mc = rmod.MiniCam(cam["W"], cam["H"], cam["fovy"], cam["fovx"], cam["viewmatrix"], cam["projmatrix"], cam["campos"])
+    out = rmod.render(mc, pc, t["bg"], device=dev)
+    assert set(out) == {"render", "viewspace_points", "visibility_filter", "radii"}
+    target = torch.rand(3, cam["H"], cam["W"], device=dev)
+    loss = (out["render"] - target).abs().mean()
+    loss.backward()
+    # oracle: same activations on the CPU, hand-derived backward, then chain rule through the activations
+    scales = torch.exp(raw["scal"].detach().cpu())
+    rots = torch.nn.functional.normalize(raw["rot"].detach().cpu())
+    opac = torch.sigmoid(raw["op"].detach().cpu())
+    sc2 = dict(sc, scales=scales.numpy(), rotations=rots.numpy(), opacities=opac.numpy())
+    o = oracle_forward(orc, sc2)
+    assert np.abs(out["render"].detach().cpu().numpy() - o["color"]).max() <= 1e-5
+    dpix = (torch.sign(out["render"].detach() - target) / target.numel()).cpu().numpy()
+    og = orc.backward(o, dpix)
+    assert_grad_close("viewspace.grad", out["viewspace_points"].grad.cpu().numpy(), og["dL_dmeans2D"])
+    assert_grad_close("xyz.grad", raw["xyz"].grad.cpu().numpy(), og["dL_dmeans3D"])
+    assert_grad_close("feat.grad", raw["feat"].grad.cpu().numpy(), og["dL_dsh"])
+    assert_grad_close("scal.grad", raw["scal"].grad.cpu().numpy(), og["dL_dscales"] * scales.numpy())
+    assert_grad_close("op.grad", raw["op"].grad.cpu().numpy(), og["dL_dopacity"] * (opac * (1 - opac)).numpy())
+    assert out["visibility_filter"].dtype == torch.bool and out["radii"].dtype == torch.int32
+    assert np.array_equal(out["radii"].cpu().numpy(), o["radii"])
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(HERE, "golden", "*.npz"))) or [None])
+def test_against_reference_golden(path, cuda_device):
+    if path is None:
+        pytest.skip("no golden fixtures committed yet")
+    import golden.make_golden as mg
+
+    z = np.load(path)
+    sc = mg.scene_from_name(str(z["scene"]))
+    dpix = mg.dpix_for(sc, int(z["dL_dpix_seed"]))
+    color, radii, st, taps, grads = run_new(sc, cuda_device, dpix=dpix)
+    assert st["num_rendered"] == int(z["R"])
+    assert np.array_equal(radii.cpu().numpy(), z["radii"])
+    for k in ("tiles_touched", "ranges", "point_list", "n_contrib"):
+        assert np.array_equal(taps[k].cpu().numpy(), z[k]), k
+    vis = z["radii"] > 0
+    for k in ("depths", "means2D", "conic_opacity", "rgb"):
+        assert np.array_equal(taps[k].cpu().numpy()[vis].view(np.uint32), z[k][vis].view(np.uint32)), k
+    assert np.abs(color.cpu().numpy() - z["color"]).max() <= 1e-6
+    assert np.abs(taps["final_T"].cpu().numpy() - z["final_T"]).max() <= 1e-6
+    for k in GRAD_NAMES:
+        assert_grad_close(k, grads[k].cpu().numpy(), z[k])
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="oracle/_ref (compiled reference) not present")
+@pytest.mark.parametrize("name", ["config1_10k_256", "head_20k_300x200", "sh3", "config2_full", "config5_view7"])
+def test_against_compiled_reference(name, cuda_device):
+    """Same B200, same inputs, the reference's own kernels: index outputs and per-Gaussian floats bit-exact,
+    colour within 1e-6, gradients within tolerance."""
+    dev = cuda_device
+    if name == "config2_full":
+        sc = scenes.head_scene()
+    elif name == "config5_view7":
+        sc = scenes.stress_scene(view=7)
+    else:
+        sc = CASES[name]()
+    cam = sc["camera"]
+    dpix = np.random.default_rng(5).standard_normal((3, cam["H"], cam["W"])).astype(np.float32)
+    color, radii, st, taps, grads = run_new(sc, dev, dpix=dpix)
+    t = scenes.to_torch(sc, dev)
+    rst = ref_loader.ref_forward(t, t["camera"], sh_degree=sc["sh_degree"])
+    assert st["num_rendered"] == rst["R"]
+    assert torch.equal(radii, rst["radii"])
+    vis = radii > 0
+    for k in ("tiles_touched", "ranges", "point_list", "n_contrib"):
+        assert torch.equal(taps[k], rst[k]), k
+    for k in ("depths", "means2D", "conic_opacity", "rgb", "cov3D"):
+        assert torch.equal(taps[k][vis].view(torch.int32), rst[k][vis].view(torch.int32)), k
+    assert torch.equal(taps["clamped"][vis], rst["clamped"][vis])
+    assert float((color - rst["color"]).abs().max()) <= 1e-6
+    assert float((taps["final_T"] - rst["final_T"]).abs().max()) <= 1e-6
+    rg = ref_loader.ref_backward(rst, torch.from_numpy(dpix).to(dev))
+    for k in GRAD_NAMES:
+        assert_grad_close(k, grads[k].cpu().numpy(), rg[k].cpu().numpy())
+
+
+@pytest.mark.parametrize("which", ["config2", "config5"])
+def test_full_size_properties(which, cuda_device):
+    """BASELINE.json sizes: size-independent invariants (the oracle check above covers small sizes)."""
+    dev = cuda_device
+    sc = scenes.head_scene() if which == "config2" else scenes.stress_scene(view=3)
+    cam = sc["camera"]
+    dpix = np.random.default_rng(9).standard_normal((3, cam["H"], cam["W"])).astype(np.float32)
+    color, radii, st, taps, grads = run_new(sc, dev, dpix=dpix)
+    P, R_ = sc["means3D"].shape[0], st["num_rendered"]
+    tt, rng, pl = taps["tiles_touched"].long(), taps["ranges"].long(), taps["point_list"].long()
+    assert int(tt.sum()) == R_ == int((rng[:, 1] - rng[:, 0]).sum())
+    assert torch.equal((tt > 0), (radii > 0))
+    # every Gaussian appears exactly tiles_touched times
+    assert torch.equal(torch.bincount(pl, minlength=P), tt)
+    # per-tile lists are sorted by (depth bits, id): keys strictly increase except across tile boundaries
+    key = (taps["depths"].view(torch.int32).long()[pl] << 32) | pl
+    inc = key[1:] > key[:-1]
+    starts = torch.zeros(R_, dtype=torch.bool, device=dev)
+    starts[rng[rng[:, 1] > rng[:, 0], 0]] = True
+    assert bool((inc | starts[1:]).all())
+    # blend invariants
+    assert float(taps["final_T"].min()) >= 0.0 and float(taps["final_T"].max()) <= 1.0
+    assert bool((taps["n_contrib"].long().view(-1, 1) >= 0).all())
+    assert torch.isfinite(color).all() and all(torch.isfinite(g).all() for g in grads.values())
+    # determinism of the forward, linearity of the backward in dL/dpixel
+    color2, radii2, st2, taps2, grads2 = run_new(sc, dev, dpix=2.0 * dpix)
+    assert torch.equal(color, color2) and torch.equal(taps["point_list"], taps2["point_list"])
+    for k in ("dL_dmeans3D", "dL_dopacity", "dL_dscales"):
+        a, b = grads[k].double() * 2.0, grads2[k].double()
+        assert float((a - b).abs().max()) <= 2e-4 * float(b.abs().max())
+    # culled Gaussians receive exactly zero gradient
+    dead = radii == 0
+    if bool(dead.any()):
+        assert float(grads["dL_dmeans3D"][dead].abs().max()) == 0.0
+
+
+def test_mark_visible_and_knn(cuda_device):
+    dev = cuda_device
+    sc = scenes.config1_scene(P=5000)
+    sc["means3D"][::3, 2] += 5.0  # push a third behind the near plane
+    t = scenes.to_torch(sc, dev)
+    rs = settings(R, t["camera"], t["bg"], 0)
+    vis = R.GaussianRasterizer(rs).markVisible(t["means3D"])
+    assert vis.dtype == torch.bool
+    assert np.array_equal(vis.cpu().numpy(), orc.mark_visible(sc["means3D"], sc["camera"]["viewmatrix"],
+                                                              sc["camera"]["projmatrix"]))
+    for P in (1, 2, 3, 4, 100, 5000, 100000):
+        pts = np.random.default_rng(P).standard_normal((P, 3)).astype(np.float32)
+        if P == 5000:
+            pts[:, 2] = 0.25  # degenerate axis
+        got = knn.distCUDA2(torch.from_numpy(pts).to(dev)).cpu().numpy()
+        ref = orc.knn_mean_dist2(pts)
+        if P < 4:
+            assert np.array_equal(got > 1e30, ref > 1e30)
+        else:
+            assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), P
+    if ref_loader.ref_knn() is not None:
+        pts = torch.from_numpy(scenes.head_scene()["means3D"]).to(dev)
+        assert torch.equal(knn.distCUDA2(pts), ref_loader.ref_knn().distCUDA2(pts))
