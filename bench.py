@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config, one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl new|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+Workload (config 2): 512x512, 100 000 Gaussians on a head-sized surface, SH degree 0, one frame = forward render
++ backward to xyz/scale/rot/opacity/SH.  A "step" is one frame; frames shard one camera per GPU, so with N ranks
+every rank renders its own frame per step and the Gaussian gradients are all-reduced over NCCL (weak scaling).
+
+value        frames/s of forward+backward through the C ABI with all inputs resident in HBM (no host sync).
+e2e          the same step through the public operator API (fateavatar_b200.render.render + autograd) with HOST
+             inputs: pinned H2D of the frame's Gaussian attributes, camera and target image, loss, backward,
+             D2H of loss + rendered image, all inside the timed region.
+roofline     dominant kernel (blend backward): algorithmic bytes (76 R + 20 W H + 8 Tn) over its
+             mean launch time measured with CUDA events on the launching stream (fs_profile_*), against the
+             measured HBM copy bandwidth in MEASURED_PEAKS.json.
+cpu_baseline the C oracle (a port of the reference's algorithm; the reference has no CPU implementation) timed on
+             the host cores for a bounded sample of the same frames.
+gpu_reference (extra) the reference's own CUDA rasterizer, built by oracle/build_ref.py, on the same GPU/frames.
+
+--impl reference runs the CPU arm only (oracle port, all host threads), as the tier contract asks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "rendered frames/sec (forward+backward) @512x512, 100k Gaussians"
+UNIT = "frames/s"
+N_RING = 8  # distinct frames (inputs + workspaces) cycled through so that every step runs on memory > L2
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="new", choices=["new", "reference"])
+    ap.add_argument("--P", type=int, default=100000)
+    ap.add_argument("--res", type=int, default=512)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--quick", action="store_true", help="device-resident arm only (used under ncu)")
+    return ap.parse_args()
+
+
+def workload_config(args):
+    return {"workload": f"config2: FateAvatar-scale head, {args.P} Gaussians, {args.res}x{args.res}, SH0, "
+                        f"forward+backward per frame", "frames_in_ring": N_RING,
+            "l2_policy": f"ring of {N_RING} distinct frames (inputs+workspaces ~45 MB each > 126 MB L2 in total)",
+            "parallelism": f"frames sharded one per GPU (dp{args.gpus}), NCCL all-reduce of Gaussian grads"}
+
+
+def make_frames(args, n, seed0=0):
+    from fateavatar_b200 import scenes
+
+    return [scenes.head_scene(seed=seed0 + i, P=args.P, W=args.res, H=args.res) for i in range(n)]
+
+
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def cpu_arm(args, frames, seconds, max_frames):
+    """Oracle forward+backward on the host cores for a bounded number of frames."""
+    import numpy as np
+
+    from oracle import oracle as orc
+
+    threads = orc.num_threads()
+    dpix = np.random.default_rng(0).standard_normal((3, args.res, args.res)).astype(np.float32)
+    t0 = time.perf_counter()
+    n = 0
+    while n < max_frames and (n < 2 or time.perf_counter() - t0 < seconds):
+        sc = frames[n % len(frames)]
+        cam = sc["camera"]
+        st = orc.forward(sc["means3D"], sc["opacities"], sc["bg"], cam["viewmatrix"], cam["projmatrix"], cam["campos"],
+                         cam["tanfovx"], cam["tanfovy"], cam["H"], cam["W"], shs=sc["shs"], sh_degree=sc["sh_degree"],
+                         scales=sc["scales"], rotations=sc["rotations"])
+        orc.backward(st, dpix)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n} frames of the same workload (oracle forward+backward, OpenMP over {threads} threads) "
+                      f"in {dt:.1f} s"}, dt / n
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        # the reference has no CPU implementation; its algorithm restated in C (oracle/) is the CPU arm
+        if rank != 0:
+            return
+        frames = make_frames(args, 2)
+        steps = max(1, min(args.steps, 40))
+        for _ in range(min(args.warmup, 2)):
+            cpu_arm(args, frames, 0.0, 1)
+        cb, s_per_frame = cpu_arm(args, frames, 1e9, steps)
+        line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+                "warmup": min(args.warmup, 2), "ms_per_step": 1000.0 * s_per_frame, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+                "config": workload_config(args), "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "reference = zjwfufu/FateAvatar's rasterizer algorithm (CUDA-only upstream) restated in C "
+                        "(oracle/splat_oracle.c), run on the host cores; rank 0 only"}
+        print(json.dumps(line), flush=True)
+        return
+
+    import numpy as np
+    import torch
+
+    from fateavatar_b200 import _lib, rasterizer as R, render as rmod, scenes
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl new needs a CUDA device (no CPU fallback exists)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- inputs resident in HBM: each rank owns its own ring of frames (its shard of the video) -------------
+    frames = make_frames(args, N_RING, seed0=100 * rank)
+    tf = [scenes.to_torch(f, dev) for f in frames]
+    rs = [R.GaussianRasterizationSettings(t["camera"]["H"], t["camera"]["W"], t["camera"]["tanfovx"],
+                                          t["camera"]["tanfovy"], t["bg"], 1.0, t["camera"]["viewmatrix"],
+                                          t["camera"]["projmatrix"], frames[0]["sh_degree"], t["camera"]["campos"],
+                                          False, False) for t in tf]
+    dpix = [torch.randn(3, args.res, args.res, device=dev) for _ in range(N_RING)]
+    P = args.P
+    # flat gradient bucket (means3D 3, means2D 3, sh 3, opacity 1, scales 3, rotations 4 per Gaussian)
+    widths = dict(means3D=3, means2D=3, sh=3, opacity=1, scales=3, rotations=4)
+    bucket = torch.zeros(P * sum(widths.values()), device=dev)
+    views, off = {}, 0
+    for k, w in widths.items():
+        views[k] = bucket[off:off + P * w]
+        off += P * w
+
+    R.set_async(True)  # no host synchronisation inside the step; overflow is checked after the timed region
+    ring = [None] * N_RING
+    launches = [0]
+
+    def step(i):
+        k = i % N_RING
+        t = tf[k]
+        color, radii, st = R.forward_raw(rs[k], t["means3D"], t["shs"], None, t["opacities"], t["scales"],
+                                         t["rotations"], None)
+        R.backward_raw(st, dpix[k], out=views)
+        if dist is not None:
+            dist.all_reduce(bucket)
+        ring[k] = st  # keeps N_RING workspaces alive => consecutive steps touch different memory
+        launches[0] = st["launches"] + st.get("launches_bwd", 0) + 2  # + 2 memset nodes
+        return color
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    sampler.stop_flag = True
+    total_ms = e0.elapsed_time(e1)
+    di = dev.index
+    R._drain_pending(R._pinned_slots(di), di, block=True)  # raises if any timed frame overflowed its workspace
+    t_ms = torch.tensor([total_ms], device=dev)
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(t_ms.item())
+    ms_per_step = total_ms / args.steps
+    value = world * args.steps / (total_ms / 1000.0)
+
+    # ---- per-kernel device times (same loop, events around every stage launch) -----------------------------
+    lib = _lib.load()
+    lib.fs_profile_enable(1)
+    _lib.profile_read()
+    for i in range(args.steps):
+        step(i)
+    torch.cuda.synchronize()
+    prof = _lib.profile_read()
+    lib.fs_profile_enable(0)
+    stage_us = {k: 1000.0 * v[0] / v[1] for k, v in prof.items() if v[1]}
+    taps = R.decode_workspace(ring[0]["workspace"], P, args.res, args.res, ring[0]["capacity"], -1)
+    Rn = int(taps["num_rendered"])
+    Tn = ((args.res + 15) // 16) ** 2
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    alg = {"blend_backward": 76 * Rn + 20 * args.res * args.res + 8 * Tn,
+           "blend_forward": 40 * Rn + 20 * args.res * args.res + 8 * Tn,
+           "preprocess": 52 * P + (40 + 12) * P,
+           "preprocess_backward": (107 + 12) * P + (64 + 12) * P}
+    traffic = {}
+    summ = os.path.join(ROOT, "profiles", "r01_summary.json")
+    if os.path.exists(summ):
+        traffic = json.load(open(summ)).get("dram_bytes_per_launch", {})
+    dom = "blend_backward"
+    ach = alg[dom] / (stage_us[dom] * 1e-6) / 1e9 if dom in stage_us else None
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": (ach / peak) if ach else None, "traffic": traffic.get(dom), "peak_source": peak_src,
+                "algorithmic_bytes": alg[dom], "kernel_us": stage_us.get(dom),
+                "note": "the blend kernels are issue/SFU bound (about 1 exp + 60-130 instructions per pixel-splat "
+                        "pair on a few MB of records), so the HBM fraction is low by construction; see DESIGN.md"}
+    kernels = {k: {"us": round(v, 2), "alg_bytes": alg.get(k),
+                   "gbs": round(alg[k] / (v * 1e-6) / 1e9, 1) if k in alg else None} for k, v in stage_us.items()}
+
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                              "ms_per_step": ms_per_step, "kernels": kernels, "quick": True}), flush=True)
+        return
+
+    # ---- e2e: public operator API, host buffers in, loss + image out --------------------------------------
+    R.set_async(False)
+    host = []
+    for f in frames:
+        cam = f["camera"]
+        h = dict(xyz=torch.from_numpy(f["means3D"]), feat=torch.from_numpy(f["shs"]),
+                 scal=torch.log(torch.from_numpy(f["scales"])), rot=torch.from_numpy(f["rotations"]),
+                 op=torch.logit(torch.from_numpy(f["opacities"])), view=torch.from_numpy(cam["viewmatrix"]),
+                 proj=torch.from_numpy(cam["projmatrix"]), campos=torch.from_numpy(cam["campos"]),
+                 bg=torch.from_numpy(f["bg"]), target=torch.rand(3, args.res, args.res))
+        host.append({k: v.contiguous().pin_memory() for k, v in h.items()})
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+    out_img = torch.empty(3, args.res, args.res).pin_memory()
+    out_loss = torch.empty(1).pin_memory()
+    d2h = out_img.numel() * 4 + 4
+    cam0 = frames[0]["camera"]
+
+    def e2e_step(i):
+        h = host[i % N_RING]
+        d = {k: v.to(dev, non_blocking=True) for k, v in h.items()}
+        leaves = [d[k].requires_grad_(True) for k in ("xyz", "feat", "scal", "rot", "op")]
+        pc = rmod.SplatCloud(*leaves, 0)
+        mc = rmod.MiniCam(cam0["W"], cam0["H"], cam0["fovy"], cam0["fovx"], d["view"], d["proj"], d["campos"])
+        out = rmod.render(mc, pc, d["bg"], device=dev)
+        loss = (out["render"] - d["target"]).abs().mean()
+        loss.backward()
+        if dist is not None:
+            for p in leaves:
+                dist.all_reduce(p.grad)
+        out_img.copy_(out["render"].detach(), non_blocking=True)
+        out_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(out_loss[0])
+
+    e2e_steps = max(10, min(args.steps, 100))
+    for i in range(5):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    e2e = {"value": world * e2e_steps / (float(t_ms.item()) / 1000.0), "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+           "api": "fateavatar_b200.render.render (mirror of volume_rendering/render_3dgs.py) + autograd, "
+                  "default synchronous mode"}
+
+    # ---- the reference's own CUDA rasterizer on the same GPU / frames (extra, rank 0) ----------------------
+    gpu_ref = None
+    if rank == 0:
+        try:
+            from oracle import ref_loader
+
+            if ref_loader.available():
+                C = ref_loader.ref_dgr()
+                e = torch.Tensor([])
+
+                def ref_step(i):
+                    k = i % N_RING
+                    t, cam = tf[k], tf[k]["camera"]
+                    a = (t["bg"], t["means3D"], e, t["opacities"], t["scales"], t["rotations"], 1.0, e,
+                         cam["viewmatrix"], cam["projmatrix"], cam["tanfovx"], cam["tanfovy"], cam["H"], cam["W"],
+                         t["shs"], 0, cam["campos"], False, False)
+                    Rr, c, rad, g, b, im = C.rasterize_gaussians(*a)
+                    C.rasterize_gaussians_backward(a[0], a[1], rad, a[2], a[4], a[5], a[6], a[7], a[8], a[9], a[10],
+                                                   a[11], dpix[k], a[14], a[15], a[16], g, Rr, b, im, False)
+
+                n_ref = max(10, min(args.steps, 100))
+                for i in range(5):
+                    ref_step(i)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()  # the reference launches on the legacy stream: wall clock + full syncs
+                for i in range(n_ref):
+                    ref_step(i)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                gpu_ref = {"value": n_ref / dt, "unit": UNIT, "ms_per_step": 1000.0 * dt / n_ref, "steps": n_ref,
+                           "what": "reference diff-gaussian-rasterization (sm_100 build, oracle/_ref) forward+backward, "
+                                   "same frames, same GPU, 1 GPU"}
+        except Exception as ex:  # never let the extra comparison break the contract line
+            gpu_ref = {"error": repr(ex)}
+
+    cb = None
+    if rank == 0 and world == 1:
+        cb, _ = cpu_arm(args, frames, args.cpu_seconds, 60)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(args), "num_rendered": Rn, "clocks": sampler.summary(), "e2e": e2e,
+                "gpu_launches": launches[0] * args.steps, "gpu_launches_per_step": launches[0], "roofline": roofline,
+                "kernels": kernels, "cpu_baseline": cb, "gpu_reference": gpu_ref,
+                "speedup_vs_gpu_reference": (value / world / gpu_ref["value"]) if gpu_ref and "value" in gpu_ref else None}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -206,9 +206,11 @@ def forward_raw(raster_settings, means3D, sh, colors_precomp, opacities, scales,
     return color, radii, state
 
 
-def backward_raw(state, grad_out_color):
+def backward_raw(state, grad_out_color, out=None):
     """One fs_backward call for a state returned by forward_raw.  Returns the reference's 8 gradient tensors
-    (means2D, colors, opacity, means3D, cov3D, sh, scales, rotations) as in rasterize_points.cu:195."""
+    (means2D, colors, opacity, means3D, cov3D, sh, scales, rotations) as in rasterize_points.cu:195.
+    `out` may map any of means3D/means2D/colors/opacity/cov3D/sh/scales/rotations to preallocated contiguous
+    float32 tensors (e.g. views of one flat all-reduce bucket) that receive the gradients in place."""
     lib = _lib.load()
     rs = state["raster_settings"]
     P, D, M, H, W = state["dims"]
@@ -216,14 +218,23 @@ def backward_raw(state, grad_out_color):
     dev = m3.device
     opts = dict(dtype=torch.float32, device=dev)
     alloc = torch.zeros if P == 0 else torch.empty  # every element is written by fs_backward when P > 0
-    g_means3D = alloc((P, 3), **opts)
-    g_means2D = alloc((P, 3), **opts)
-    g_colors = alloc((P, 3), **opts)
-    g_opacity = alloc((P, 1), **opts)
-    g_cov3D = alloc((P, 6), **opts)
-    g_sh = alloc((P, M, 3), **opts)
-    g_scales = alloc((P, 3), **opts)
-    g_rot = alloc((P, 4), **opts)
+    out = out or {}
+
+    def buf(name, shape):
+        t = out.get(name)
+        if t is None:
+            return alloc(shape, **opts)
+        assert t.is_contiguous() and t.dtype == torch.float32 and t.numel() == int(torch.Size(shape).numel()), name
+        return t.view(shape)
+
+    g_means3D = buf("means3D", (P, 3))
+    g_means2D = buf("means2D", (P, 3))
+    g_colors = buf("colors", (P, 3))
+    g_opacity = buf("opacity", (P, 1))
+    g_cov3D = buf("cov3D", (P, 6))
+    g_sh = buf("sh", (P, M, 3))
+    g_scales = buf("scales", (P, 3))
+    g_rot = buf("rotations", (P, 4))
     if P != 0:
         if grad_out_color.dtype != torch.float32:
             grad_out_color = grad_out_color.float()

@@ -368,10 +368,14 @@ static inline float splat_power(float mx, float my, float pxf, float pyf, float 
     return fmaf(q, -0.5f, -(ddy * (ddx * cy)));
 }
 
-/* forward.cu:261-374 */
+/* forward.cu:261-374.
+ * `fragile` (optional, [H*W]) is set for pixels where one of the rule's three discrete decisions
+ * (power > 0, alpha < 1/255, T(1-alpha) < 1e-4) was within rounding distance of its threshold: there a 1-ulp
+ * difference between glibc's expf and CUDA's MUFU-based expf can flip the decision, so tests compare such
+ * pixels with the looser bound of one dropped 1/255 contribution instead of 1e-5. */
 void orc_blend_forward(int W, int H, const uint32_t* ranges, const uint32_t* point_list, const float* means2D,
                        const float* colors, const float* conic_opacity, const float* bg, float* out_color,
-                       float* final_T, uint32_t* n_contrib) {
+                       float* final_T, uint32_t* n_contrib, uint8_t* fragile) {
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
 #pragma omp parallel for schedule(dynamic, 1)
     for (int t = 0; t < gx * gy; ++t) {
@@ -384,16 +388,20 @@ void orc_blend_forward(int W, int H, const uint32_t* ranges, const uint32_t* poi
                 const float pxf = (float)x, pyf = (float)y;
                 float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
                 uint32_t contributor = 0, last = 0;
+                uint8_t frag = 0;
                 for (uint32_t j = r0; j < r1; ++j) {
                     contributor++;
                     const uint32_t g = point_list[j];
                     const float* co = conic_opacity + 4 * (size_t)g;
                     float dx, dy;
                     float power = splat_power(means2D[2 * g], means2D[2 * g + 1], pxf, pyf, co[0], co[1], co[2], &dx, &dy);
+                    if (fabsf(power) < 1e-6f) frag = 1;
                     if (power > 0.0f) continue;
                     float alpha = fminf(0.99f, co[3] * expf(power));
+                    if (fabsf(alpha - 1.0f / 255.0f) < 4e-8f) frag = 1;
                     if (alpha < 1.0f / 255.0f) continue;
                     float test_T = T * (1.0f - alpha);
+                    if (fabsf(test_T - 0.0001f) < 2e-8f) frag = 1;
                     if (test_T < 0.0001f) break;
                     const float* c = colors + 3 * (size_t)g;
                     C0 = fmaf(T, alpha * c[0], C0);
@@ -405,6 +413,7 @@ void orc_blend_forward(int W, int H, const uint32_t* ranges, const uint32_t* poi
                 const size_t pid = (size_t)y * W + x;
                 final_T[pid] = T;
                 n_contrib[pid] = last;
+                if (fragile) fragile[pid] = frag;
                 out_color[pid] = fmaf(bg[0], T, C0);
                 out_color[(size_t)H * W + pid] = fmaf(bg[1], T, C1);
                 out_color[2 * (size_t)H * W + pid] = fmaf(bg[2], T, C2);

@@ -51,10 +51,9 @@ def check_forward_vs_oracle(color, radii, st, taps, o):
         got = taps[k].cpu().numpy()[vis]
         assert np.array_equal(got.view(np.uint32), o[k][vis].view(np.uint32)), f"{k} not bit-exact"
     assert np.array_equal(taps["clamped"].cpu().numpy()[vis], o["clamped"][vis])
-    nc = taps["n_contrib"].cpu().numpy()
-    assert (nc != o["n_contrib"].astype(np.int32)).mean() <= 1e-4
-    assert np.abs(taps["final_T"].cpu().numpy() - o["final_T"]).max() <= 1e-5
-    assert np.abs(color.cpu().numpy() - o["color"]).max() <= 1e-5  # north_star bar: 1e-4
+    # 1e-5 on every pixel whose discrete decisions are not within rounding distance of a threshold (north_star
+    # bar: 1e-4); see oracle.compare_blend for the handling of the (rare) threshold-fragile pixels
+    orc.compare_blend(o, color.cpu().numpy(), taps["final_T"].cpu().numpy(), taps["n_contrib"].cpu().numpy())
 
 
 CASES = {
@@ -103,7 +102,7 @@ def test_colors_precomp_cov3d_precomp_scale_modifier_black_bg(cuda_device):
     # precomputed colours (monogaussianavatar.py:411-421 variant)
     color, radii, st, taps, grads = run_new(sc, cuda_device, colors_precomp=col, dpix=dpix)
     o = oracle_forward(orc, sc, shs=None, colors_precomp=col)
-    assert np.abs(color.cpu().numpy() - o["color"]).max() <= 1e-5
+    orc.compare_blend(o, color.cpu().numpy())
     og = orc.backward(o, dpix)
     for k in ("dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dscales", "dL_drotations", "dL_dmeans2D"):
         assert_grad_close(k, grads[k].cpu().numpy(), og[k])
@@ -180,7 +179,7 @@ def test_autograd_through_render_mirror(cuda_device):
     opac = torch.sigmoid(raw["op"].detach().cpu())
     sc2 = dict(sc, scales=scales.numpy(), rotations=rots.numpy(), opacities=opac.numpy())
     o = oracle_forward(orc, sc2)
-    assert np.abs(out["render"].detach().cpu().numpy() - o["color"]).max() <= 1e-5
+    orc.compare_blend(o, out["render"].detach().cpu().numpy())
     dpix = (torch.sign(out["render"].detach() - target) / target.numel()).cpu().numpy()
     og = orc.backward(o, dpix)
     assert_grad_close("viewspace.grad", out["viewspace_points"].grad.cpu().numpy(), og["dL_dmeans2D"])
