@@ -105,7 +105,7 @@ void fs_compute_layout(int P, int W, int H, size_t Rcap, fs_workspace_layout* L)
         return o;
     };
     memset(L, 0, sizeof(*L));
-    L->info = take(sizeof(fs_frame_info));
+    L->info = take(sizeof(fs_frame_info) + 1024);  // header + 256 per-SM slot counters of the forward blend
     L->tile_count = take(Tn * 4 * FS_CNT_STRIDE);  // directly after the header: one memset clears both
     L->tile_cursor = take(Tn * 4 * FS_CNT_STRIDE);
     L->ranges = take(Tn * 8);
@@ -123,7 +123,7 @@ void fs_compute_layout(int P, int W, int H, size_t Rcap, fs_workspace_layout* L)
     L->inst_splat = take(Rcap * 48);
     L->final_T = take((size_t)W * H * 4);
     L->n_contrib = take((size_t)W * H * 4);
-    L->bwd_counter = take(256);
+    L->bwd_counter = take(256 + 1024);  // work counter + 256 per-SM slot counters of the backward blend
     L->grad_acc = take(Pn * 48);
     L->instance_capacity = Rcap;
     L->total_bytes = off;

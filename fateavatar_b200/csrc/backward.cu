@@ -62,7 +62,8 @@ struct WarpStage {
 // Persistent warps pull (tile, 8x4 block) units heaviest-first, exactly like the forward kernel.
 __global__ void __launch_bounds__(kWarps * 32)
 blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ work_order,
-                      const uint32_t* __restrict__ n_nonempty_tiles, uint32_t* __restrict__ work_counter,
+                      const uint32_t* __restrict__ n_nonempty_tiles, uint32_t sm_count,
+                      uint32_t* __restrict__ sm_slots, uint32_t* __restrict__ work_counter,
                       const SplatRec* __restrict__ inst_splat, int W, int H, const float* __restrict__ bg_color,
                       const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                       const float* __restrict__ dL_dpix, float* __restrict__ grad_acc, uint32_t Rcap) {
@@ -71,6 +72,19 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sizeof(WarpStage) * kWarps);
 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    {   // keep ~2 dense units per active warp (see blend_forward.cu); surplus CTAs retire immediately
+        const uint32_t dense_units = __ldg(n_nonempty_tiles) * 8u;
+        const uint32_t want_per_sm = max(1u, dense_units / (2u * kWarps * sm_count));
+        // placement-independent: the k-th CTA to arrive on an SM stays iff k < want_per_sm
+        __shared__ uint32_t s_rank;
+        if (threadIdx.x == 0) {
+            uint32_t smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            s_rank = atomicAdd(&sm_slots[smid & 255u], 1u);
+        }
+        __syncthreads();
+        if (s_rank >= want_per_sm) return;
+    }
     SplatRec(*rec_ring)[kBatch] = stages[wid].rec;
     uint64_t* s_full = bars + wid * 2;
     if (lane == 0) {
@@ -506,11 +520,12 @@ void fs_launch_backward(int P, int D, int M, const float* bg, int W, int H, cons
             attr_set = true;
         }
         auto* info = reinterpret_cast<fs_frame_info*>(ws + L.info);
-        const int ctas_per_sm = fs_tuning("FATESPLAT_BWD_CTAS_PER_SM", 1);
-        const int grid = min(fs_num_sms() * ctas_per_sm, (gx * gy * 8 + kWarps - 1) / kWarps);
+        const int ctas_per_sm = fs_tuning("FATESPLAT_BWD_CTAS_PER_SM", 2);  // upper bound (100 regs/thread)
+        const int grid = fs_num_sms() * ctas_per_sm;
         blend_backward_kernel<<<grid, kWarps * 32, smem, stream>>>(
             reinterpret_cast<const uint2*>(ws + L.ranges), reinterpret_cast<const uint32_t*>(ws + L.work_order),
-            &info->reserved[3], reinterpret_cast<uint32_t*>(ws + L.bwd_counter),
+            &info->reserved[3], (uint32_t)fs_num_sms(), reinterpret_cast<uint32_t*>(ws + L.bwd_counter + 256),
+            reinterpret_cast<uint32_t*>(ws + L.bwd_counter),
             reinterpret_cast<const SplatRec*>(ws + L.inst_splat), W, H, bg,
             reinterpret_cast<const float*>(ws + L.final_T), reinterpret_cast<const uint32_t*>(ws + L.n_contrib),
             dL_dpix, grad_acc, (uint32_t)L.instance_capacity);

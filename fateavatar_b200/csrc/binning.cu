@@ -159,9 +159,12 @@ __device__ __forceinline__ void bitonic_sort_ascending(u64* s, uint32_t n, int t
 }
 
 // ---- linear-bucket sort of one tile segment held in shared memory ------------------------------------------
-// s_in[n] unsorted keys -> s_out[n] sorted.  PER = ceil(CAP / THREADS) keys per thread.
+// Keys are unique (they embed the Gaussian id), so after the keys are grouped by depth bucket every key's final
+// position is  bucket_start + #(keys of the same bucket that are smaller): one short, fully parallel scan of
+// the key's own bucket -- no serial insertion tail.  s_grp[n] = bucket-grouped keys, s_fin[n] = sorted result.
+// PER = ceil(CAP / THREADS) keys per thread.
 template <int THREADS, int PER, int MAXB>
-__device__ __forceinline__ void bucket_sort(const u64* __restrict__ gkeys, uint32_t n, u64* s_in, u64* s_out,
+__device__ __forceinline__ void bucket_sort(const u64* __restrict__ gkeys, uint32_t n, u64* s_grp, u64* s_fin,
                                             uint32_t* s_cnt, uint32_t* s_red) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     constexpr int NW = THREADS / 32;
@@ -249,27 +252,27 @@ __device__ __forceinline__ void bucket_sort(const u64* __restrict__ gkeys, uint3
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
         const uint32_t i = tid + k * THREADS;
-        if (i < n) s_out[s_cnt[br[k] & 0xffffu] + (br[k] >> 16)] = mine[k];
+        if (i < n) s_grp[s_cnt[br[k] & 0xffffu] + (br[k] >> 16)] = mine[k];
     }
     __syncthreads();
-    if (maxb <= 48) {
-        for (uint32_t b = tid; b < nb; b += THREADS) {  // insertion sort inside each (tiny) bucket
-            const uint32_t lo = s_cnt[b], hi = s_cnt[b + 1];
-            for (uint32_t i = lo + 1; i < hi; ++i) {
-                const u64 v = s_out[i];
-                uint32_t j = i;
-                while (j > lo && s_out[j - 1] > v) {
-                    s_out[j] = s_out[j - 1];
-                    --j;
-                }
-                s_out[j] = v;
+    if (maxb <= 512) {
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const uint32_t i = tid + k * THREADS;
+            if (i < n) {
+                const uint32_t b = br[k] & 0xffffu;
+                const uint32_t lo = s_cnt[b], hi = s_cnt[b + 1];
+                uint32_t rank = lo;
+                for (uint32_t j = lo; j < hi; ++j) rank += (s_grp[j] < mine[k]) ? 1u : 0u;
+                s_fin[rank] = mine[k];
             }
         }
         __syncthreads();
-    } else {
-        bitonic_sort_ascending(s_out, n, tid, THREADS);  // skewed depth distribution: still exact, just slower
+    } else {  // one bucket holds most keys (extreme depth outliers): still exact, just slower
+        bitonic_sort_ascending(s_grp, n, tid, THREADS);
+        for (uint32_t i = tid; i < n; i += THREADS) s_fin[i] = s_grp[i];
+        __syncthreads();
     }
-    (void)s_in;
 }
 
 // write sorted ids and gather the splat records into sorted order (coalesced 16-byte stores)
@@ -290,13 +293,14 @@ constexpr int kSortPer = FS_SORT_SMEM_CAP / kSortThreads;
 __global__ void __launch_bounds__(kSortThreads)
 tile_sort_kernel(const uint2* __restrict__ ranges, const u64* __restrict__ keys, const float4* __restrict__ splat,
                  uint32_t* __restrict__ point_list, float4* __restrict__ inst_splat, uint32_t Rcap) {
+    __shared__ u64 s_grp[FS_SORT_SMEM_CAP];
     __shared__ u64 s_out[FS_SORT_SMEM_CAP];
     __shared__ uint32_t s_cnt[FS_SORT_SMEM_CAP + 1];
     __shared__ uint32_t s_red[2 * (kSortThreads / 32)];
     const uint2 r = ranges[blockIdx.x];
     const uint32_t n = r.y - r.x;
     if (n == 0 || n > FS_SORT_SMEM_CAP || r.y > Rcap) return;
-    bucket_sort<kSortThreads, kSortPer, FS_SORT_SMEM_CAP>(keys + r.x, n, nullptr, s_out, s_cnt, s_red);
+    bucket_sort<kSortThreads, kSortPer, FS_SORT_SMEM_CAP>(keys + r.x, n, s_grp, s_out, s_cnt, s_red);
     emit_sorted(s_out, n, r.x, splat, point_list, inst_splat, threadIdx.x, kSortThreads);
 }
 
@@ -319,9 +323,10 @@ big_tile_sort_kernel(const uint32_t* __restrict__ big_tiles, const uint2* __rest
         const uint32_t n = r.y - r.x;
         if (r.y > Rcap) continue;
         if (n <= kBigBucketCap) {
-            u64* s_out = d_smem;                                                  // 64 KB
-            uint32_t* s_cnt = reinterpret_cast<uint32_t*>(d_smem + kBigBucketCap);  // 32 KB + 4
-            bucket_sort<kBigThreads, kBigBucketCap / kBigThreads, kBigBucketCap>(keys + r.x, n, nullptr, s_out, s_cnt,
+            u64* s_grp = d_smem;                                                      // 64 KB
+            u64* s_out = d_smem + kBigBucketCap;                                      // 64 KB
+            uint32_t* s_cnt = reinterpret_cast<uint32_t*>(d_smem + 2 * kBigBucketCap);  // 32 KB + 4
+            bucket_sort<kBigThreads, kBigBucketCap / kBigThreads, kBigBucketCap>(keys + r.x, n, s_grp, s_out, s_cnt,
                                                                                s_red);
             emit_sorted(s_out, n, r.x, splat, point_list, inst_splat, threadIdx.x, kBigThreads);
         } else if (n <= kBigSmemCap) {

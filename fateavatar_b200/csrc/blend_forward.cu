@@ -33,9 +33,67 @@ struct WarpStage {
     SplatRec rec[kStages][kBatch];
 };
 
+struct Group {
+    float alpha[kGroup];  // < 0: skip (not a survivor, power > 0, or alpha < 1/255)
+    float4 col[kGroup];
+    int jj[kGroup];
+    bool any;
+};
+__device__ __forceinline__ bool cur_valid(const Group& g) { return g.any; }
+
+// extract the next (up to) four set bits of m and evaluate alpha for this lane's pixel
+__device__ __forceinline__ void compute_group(Group& g, unsigned& m, int c, const SplatRec* __restrict__ rec, float pxf,
+                                              float pyf) {
+    bool live[kGroup];
+#pragma unroll
+    for (int k = 0; k < kGroup; ++k) {  // branch-free extraction
+        const int fbit = __ffs(m);
+        live[k] = fbit != 0;
+        g.jj[k] = live[k] ? c + fbit - 1 : c;
+        m &= m - 1;
+    }
+    float4 q0[kGroup], q1[kGroup];
+#pragma unroll
+    for (int k = 0; k < kGroup; ++k) {
+        q0[k] = rec[g.jj[k]].q0;
+        q1[k] = rec[g.jj[k]].q1;
+        g.col[k] = rec[g.jj[k]].q2;
+    }
+#pragma unroll
+    for (int k = 0; k < kGroup; ++k) {
+        const float dx = fs::sub(q0[k].x, pxf), dy = fs::sub(q0[k].y, pyf);
+        const float power = fs::splat_power(dx, dy, q1[k].x, q1[k].y, q1[k].z);
+        const float a = fminf(0.99f, fs::mul(q1[k].w, expf(power)));
+        g.alpha[k] = (live[k] && power <= 0.0f && a >= 1.0f / 255.0f) ? a : -1.0f;
+    }
+    g.any = true;
+}
+
+// sequential transmittance update (front-to-back order), fully predicated
+__device__ __forceinline__ void apply_group(const Group& g, uint32_t base, float& T, float& C0, float& C1, float& C2,
+                                            bool& done, uint32_t& last_contributor) {
+#pragma unroll
+    for (int k = 0; k < kGroup; ++k) {
+        const float test_T = fs::mul(T, fs::sub(1.0f, g.alpha[k]));
+        const bool act = g.alpha[k] >= 0.0f && !done;
+        const bool stop = act && test_T < 0.0001f;
+        const bool apply = act && !stop;
+        done = done || stop;
+        const float n0 = fs::mad(T, fs::mul(g.alpha[k], g.col[k].x), C0);
+        const float n1 = fs::mad(T, fs::mul(g.alpha[k], g.col[k].y), C1);
+        const float n2 = fs::mad(T, fs::mul(g.alpha[k], g.col[k].z), C2);
+        C0 = apply ? n0 : C0;
+        C1 = apply ? n1 : C1;
+        C2 = apply ? n2 : C2;
+        T = apply ? test_T : T;
+        last_contributor = apply ? base + (uint32_t)g.jj[k] + 1u : last_contributor;
+    }
+}
+
 __global__ void __launch_bounds__(kWarps * 32)
 blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ work_order, int n_tiles,
-                     uint32_t* __restrict__ work_counter, const SplatRec* __restrict__ inst_splat, int W, int H,
+                     const uint32_t* __restrict__ n_nonempty_tiles, uint32_t sm_count,
+                     uint32_t* __restrict__ sm_slots, uint32_t* __restrict__ work_counter, const SplatRec* __restrict__ inst_splat, int W, int H,
                      const float* __restrict__ bg_color, float* __restrict__ out_color, float* __restrict__ final_T,
                      uint32_t* __restrict__ n_contrib, uint32_t Rcap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -43,6 +101,22 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sizeof(WarpStage) * kWarps);
 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // Dynamic balancing needs clearly more heavy units than warps (a warp that owns a single dense unit is
+    // the critical path), so only as many CTAs stay active as there are ~2 dense units per warp; the launch
+    // is sized for the largest case and surplus CTAs retire immediately.  CTA i runs on SM (i mod #SM).
+    {
+        const uint32_t dense_units = __ldg(n_nonempty_tiles) * 8u;
+        const uint32_t want_per_sm = max(1u, dense_units / (2u * kWarps * sm_count));
+        // placement-independent: the k-th CTA to arrive on an SM stays iff k < want_per_sm
+        __shared__ uint32_t s_rank;
+        if (threadIdx.x == 0) {
+            uint32_t smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            s_rank = atomicAdd(&sm_slots[smid & 255u], 1u);
+        }
+        __syncthreads();
+        if (s_rank >= want_per_sm) return;
+    }
     SplatRec(*rec_ring)[kBatch] = stages[wid].rec;
     uint64_t* s_full = bars + wid * kStages;
     if (lane == 0) {
@@ -107,66 +181,16 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                           !(q0.x + q0.z < wx0 || q0.x - q0.z > wx1 || q0.y + q0.w < wy0 || q0.y - q0.w > wy1);
                 }
                 unsigned m = __ballot_sync(0xffffffffu, hit);
-                // Walk the survivors four at a time: the four power/exp chains are independent and overlap;
-                // only the short transmittance update below is sequential (front-to-back order preserved).
+                // Survivors are walked four at a time.  The vote ends the basic block, so all four alphas are
+                // needed at once and the scheduler overlaps the four power/exp chains instead of trailing them
+                // behind the (short, sequential) transmittance chain; it also skips groups that touch no pixel.
                 while (m) {
-                    int jj[kGroup];
-                    bool live[kGroup];
-                    float alpha[kGroup];
-                    float4 col[kGroup];
-#pragma unroll
-                    for (int k = 0; k < kGroup; ++k) {  // branch-free extraction of the next four set bits
-                        const int fbit = __ffs(m);
-                        live[k] = fbit != 0;
-                        jj[k] = live[k] ? c + fbit - 1 : c;
-                        m &= m - 1;
-                    }
-                    // stage-wise formulation: each statement group is independent across k, so the four chains
-                    // issue interleaved instead of back to back
-                    float4 q0[kGroup], q1[kGroup];
-#pragma unroll
-                    for (int k = 0; k < kGroup; ++k) {
-                        q0[k] = rec[jj[k]].q0;
-                        q1[k] = rec[jj[k]].q1;
-                        col[k] = rec[jj[k]].q2;
-                    }
-                    float power[kGroup];
-#pragma unroll
-                    for (int k = 0; k < kGroup; ++k) {
-                        const float dx = fs::sub(q0[k].x, pxf), dy = fs::sub(q0[k].y, pyf);
-                        power[k] = fs::splat_power(dx, dy, q1[k].x, q1[k].y, q1[k].z);
-                    }
-                    float ex[kGroup];
-#pragma unroll
-                    for (int k = 0; k < kGroup; ++k) ex[k] = expf(power[k]);
-#pragma unroll
-                    for (int k = 0; k < kGroup; ++k) {
-                        const float a = fminf(0.99f, fs::mul(q1[k].w, ex[k]));
-                        // alpha < 0 marks "skip": not a survivor, power > 0, or alpha < 1/255
-                        alpha[k] = (live[k] && power[k] <= 0.0f && a >= 1.0f / 255.0f) ? a : -1.0f;
-                    }
-                    // The vote ends the basic block: all four alphas are needed here, so the scheduler overlaps
-                    // the four chains instead of trailing them behind the transmittance chain below.  It also
-                    // skips the update when no pixel of the block is touched by this group.
-                    if (!__any_sync(0xffffffffu, (alpha[0] >= 0.0f) | (alpha[1] >= 0.0f) | (alpha[2] >= 0.0f) |
-                                                     (alpha[3] >= 0.0f)))
+                    Group g;
+                    compute_group(g, m, c, rec, pxf, pyf);
+                    if (!__any_sync(0xffffffffu, (g.alpha[0] >= 0.0f) | (g.alpha[1] >= 0.0f) | (g.alpha[2] >= 0.0f) |
+                                                     (g.alpha[3] >= 0.0f)))
                         continue;
-#pragma unroll
-                    for (int k = 0; k < kGroup; ++k) {  // sequential transmittance update, predicated (no branches)
-                        const float test_T = fs::mul(T, fs::sub(1.0f, alpha[k]));
-                        const bool act = alpha[k] >= 0.0f && !done;
-                        const bool stop = act && test_T < 0.0001f;
-                        const bool apply = act && !stop;
-                        done = done || stop;
-                        const float n0 = fs::mad(T, fs::mul(alpha[k], col[k].x), C0);
-                        const float n1 = fs::mad(T, fs::mul(alpha[k], col[k].y), C1);
-                        const float n2 = fs::mad(T, fs::mul(alpha[k], col[k].z), C2);
-                        C0 = apply ? n0 : C0;
-                        C1 = apply ? n1 : C1;
-                        C2 = apply ? n2 : C2;
-                        T = apply ? test_T : T;
-                        last_contributor = apply ? (uint32_t)b * kBatch + (uint32_t)jj[k] + 1u : last_contributor;
-                    }
+                    apply_group(g, (uint32_t)b * kBatch, T, C0, C1, C2, done, last_contributor);
                 }
                 warp_done = __all_sync(0xffffffffu, done);
             }
@@ -208,11 +232,11 @@ void fs_launch_blend_forward(int W, int H, const float* bg, float* out_color, ch
         attr_set = true;
     }
     auto* info = reinterpret_cast<fs_frame_info*>(ws + L.info);
-    const int ctas_per_sm = fs_tuning("FATESPLAT_FWD_CTAS_PER_SM", 1);
-    const int grid = min(fs_num_sms() * ctas_per_sm, (gx * gy * 8 + kWarps - 1) / kWarps);
+    const int ctas_per_sm = fs_tuning("FATESPLAT_FWD_CTAS_PER_SM", 4);  // upper bound; see the kernel prologue
+    const int grid = fs_num_sms() * ctas_per_sm;
     blend_forward_kernel<<<grid, kWarps * 32, smem, stream>>>(
         reinterpret_cast<const uint2*>(ws + L.ranges), reinterpret_cast<const uint32_t*>(ws + L.work_order), gx * gy,
-        &info->reserved[1], reinterpret_cast<const SplatRec*>(ws + L.inst_splat), W, H, bg, out_color,
+        &info->reserved[3], (uint32_t)fs_num_sms(), reinterpret_cast<uint32_t*>(info + 1), &info->reserved[1], reinterpret_cast<const SplatRec*>(ws + L.inst_splat), W, H, bg, out_color,
         reinterpret_cast<float*>(ws + L.final_T), reinterpret_cast<uint32_t*>(ws + L.n_contrib),
         (uint32_t)L.instance_capacity);
     fs_count_launch(1);

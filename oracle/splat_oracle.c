@@ -370,7 +370,7 @@ static inline float splat_power(float mx, float my, float pxf, float pyf, float 
 
 /* forward.cu:261-374.
  * `fragile` (optional, [H*W]) is set for pixels where one of the rule's three discrete decisions
- * (power > 0, alpha < 1/255, T(1-alpha) < 1e-4) was within rounding distance of its threshold: there a 1-ulp
+ * that involve expf (alpha < 1/255, T(1-alpha) < 1e-4) was within rounding distance of its threshold: there a 1-ulp
  * difference between glibc's expf and CUDA's MUFU-based expf can flip the decision, so tests compare such
  * pixels with the looser bound of one dropped 1/255 contribution instead of 1e-5. */
 void orc_blend_forward(int W, int H, const uint32_t* ranges, const uint32_t* point_list, const float* means2D,
@@ -395,13 +395,12 @@ void orc_blend_forward(int W, int H, const uint32_t* ranges, const uint32_t* poi
                     const float* co = conic_opacity + 4 * (size_t)g;
                     float dx, dy;
                     float power = splat_power(means2D[2 * g], means2D[2 * g + 1], pxf, pyf, co[0], co[1], co[2], &dx, &dy);
-                    if (fabsf(power) < 1e-6f) frag = 1;
                     if (power > 0.0f) continue;
                     float alpha = fminf(0.99f, co[3] * expf(power));
-                    if (fabsf(alpha - 1.0f / 255.0f) < 4e-8f) frag = 1;
+                    if (fabsf(alpha - 1.0f / 255.0f) < 1e-8f) frag = 1; /* expf differs by <= 3 ulp: |d alpha| < 2e-9 */
                     if (alpha < 1.0f / 255.0f) continue;
                     float test_T = T * (1.0f - alpha);
-                    if (fabsf(test_T - 0.0001f) < 2e-8f) frag = 1;
+                    if (fabsf(test_T - 0.0001f) < 3e-9f) frag = 1;
                     if (test_T < 0.0001f) break;
                     const float* c = colors + 3 * (size_t)g;
                     C0 = fmaf(T, alpha * c[0], C0);
