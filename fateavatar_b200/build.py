@@ -38,7 +38,8 @@ def build(force=False, verbose=False):
         return OUT
     os.makedirs(OUT_DIR, exist_ok=True)
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", OUT]
+    extra = os.environ.get("FATESPLAT_NVCC_DEFINES", "").split()  # experiment knobs, e.g. -DFS_FWD_GROUP=8
+    cmd = ["nvcc"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", OUT]
     print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)
     return OUT
