@@ -37,7 +37,7 @@ class FsWorkspaceLayout(C.Structure):
 EXPORTS = [
     "fs_workspace_bytes", "fs_get_workspace_layout", "fs_forward", "fs_backward", "fs_mark_visible",
     "fs_knn_workspace_bytes", "fs_knn_mean_dist2", "fs_last_launch_count", "fs_last_error", "fs_version",
-    "fs_profile_enable", "fs_profile_read",
+    "fs_profile_enable", "fs_profile_read", "fs_pose_forward", "fs_pose_backward",
 ]
 
 STAGES = ["preprocess", "tile_scan", "scatter", "tile_sort", "big_tile_sort", "blend_forward", "blend_backward",
@@ -78,6 +78,10 @@ def load():
     lib.fs_knn_workspace_bytes.argtypes = [i]
     lib.fs_knn_mean_dist2.restype = i
     lib.fs_knn_mean_dist2.argtypes = [i, vp, vp, vp, sz, vp]
+    lib.fs_pose_forward.restype = i
+    lib.fs_pose_forward.argtypes = [i, i, i] + [vp] * 9 + [f, i] + [vp] * 4 + [vp]
+    lib.fs_pose_backward.restype = i
+    lib.fs_pose_backward.argtypes = [i, i, i] + [vp] * 9 + [f, i] + [vp] * 4 + [vp] * 5 + [vp]
     lib.fs_profile_enable.restype = None
     lib.fs_profile_enable.argtypes = [i]
     lib.fs_profile_read.restype = i

@@ -153,3 +153,46 @@ def to_torch(scene, device):
         else:
             out[k] = v
     return out
+
+
+def ellipsoid_mesh(n_lat=51, n_lon=100, semi=(0.105, 0.155, 0.11)):
+    """Closed triangle mesh with FLAME-like size (V = (n_lat-1)*n_lon + 2 = 5002, F = 2*n_lon*(n_lat-1) = 10000
+    by default): stand-in for the licensed FLAME template in the pose-stage tests and benchmarks."""
+    verts = [(0.0, 1.0, 0.0)]
+    for i in range(1, n_lat):
+        th = math.pi * i / n_lat
+        for j in range(n_lon):
+            ph = 2 * math.pi * j / n_lon
+            verts.append((math.sin(th) * math.cos(ph), math.cos(th), math.sin(th) * math.sin(ph)))
+    verts.append((0.0, -1.0, 0.0))
+    verts = np.asarray(verts, np.float64) * np.asarray(semi)
+    faces = []
+    ring = lambda i, j: 1 + (i - 1) * n_lon + (j % n_lon)
+    for j in range(n_lon):
+        faces.append((0, ring(1, j + 1), ring(1, j)))
+        faces.append((len(verts) - 1, ring(n_lat - 1, j), ring(n_lat - 1, j + 1)))
+    for i in range(1, n_lat - 1):
+        for j in range(n_lon):
+            a, b, c, d = ring(i, j), ring(i, j + 1), ring(i + 1, j), ring(i + 1, j + 1)
+            faces.append((a, b, c))
+            faces.append((b, d, c))
+    return verts.astype(np.float32), np.asarray(faces, np.int64)
+
+
+def pose_inputs(N=100000, seed=0):
+    """Synthetic inputs of the per-splat pose stage: a posed mesh (canonical ellipsoid + smooth deformation),
+    N splat sites (face_index, barycentrics) and raw per-splat parameters as FateAvatar stores them."""
+    rng = np.random.default_rng(seed)
+    canon_verts, faces = ellipsoid_mesh()
+    bend = 0.08 * np.sin(6.0 * canon_verts[:, [1, 2, 0]]) * canon_verts + 0.002 * rng.standard_normal(canon_verts.shape)
+    verts = (canon_verts + bend).astype(np.float32)
+    face_index = rng.integers(0, faces.shape[0], N).astype(np.int64)
+    bary = rng.dirichlet(np.ones(3), N).astype(np.float32)
+    return dict(
+        verts=verts, canon_verts=canon_verts, faces=faces, face_index=face_index, bary=bary,
+        scaling_raw=np.log(np.full((N, 3), 8e-4)).astype(np.float32) + 0.3 * rng.standard_normal((N, 3)).astype(np.float32),
+        rotation_raw=(np.array([1, 0, 0, 0], np.float32) + 0.5 * rng.standard_normal((N, 4))).astype(np.float32),
+        offset_raw=(0.5 * rng.standard_normal((N, 1))).astype(np.float32),
+        opacity_raw=rng.standard_normal((N, 1)).astype(np.float32),
+        shell_len=0.05,
+    )

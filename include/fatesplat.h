@@ -13,6 +13,8 @@
  *   fs_mark_visible   <- CudaRasterizer::Rasterizer::markVisible DGR rasterizer.h:28-33, rasterizer_impl.cu:141-154;
  *                        markVisible, rasterize_points.cu:198-217 (ext.cpp:17)
  *   fs_knn_mean_dist2 <- SimpleKNN::knn  simple-knn/simple_knn.h, simple_knn.cu:186-222; distCUDA2, spatial.cu:15-26
+ *   fs_pose_forward / fs_pose_backward <- the per-frame torch ops of model/fateavatar.py:225-258 (no native
+ *                        counterpart upstream; see the declaration below)
  *
  * Differences from the reference native surface, all deliberate:
  *   - plain C, raw device pointers and sizes, explicit stream, no torch/glm/std::function types;
@@ -119,6 +121,29 @@ int fs_mark_visible(int P, const float* d_means3D, const float* d_viewmatrix, co
 size_t fs_knn_workspace_bytes(int P);
 int fs_knn_mean_dist2(int P, const float* d_points, float* d_mean_dist2, void* d_workspace, size_t workspace_bytes,
                       void* stream);
+
+/*
+ * Per-splat pose stage: mesh vertices -> the four activated tensors render() hands to
+ * the rasterizer.  Replaces, fused into one kernel per direction, model/fateavatar.py:225-240,253-258,
+ * volume_rendering/mesh_compute.py:18-59 (face frame / scale / normal), mesh_sampling.py:171-200 (barycentric
+ * position), pytorch3d matrix_to_quaternion + quaternion_multiply, and the GaussianModel activations
+ * (gaussian_model.py:105-128).  faces / face_index are int64 as in the reference's buffers.
+ *   forward : means3D [N,3], scales [N,3] = exp(_scaling + log(face_scale/canonical)), rotations [N,4] =
+ *             normalize(q_face (x) _rotation), opacities [N] = sigmoid(_opacity)
+ *   backward: dL/dverts [V,3] (zero-filled here, then accumulated) and dL/d{_scaling,_rotation,_offset,_opacity}
+ */
+int fs_pose_forward(int N, int V, int F, const float* d_verts, const long long* d_faces,
+                    const long long* d_face_index, const float* d_bary, const float* d_face_scale_canonical,
+                    const float* d_scaling_raw, const float* d_rotation_raw, const float* d_offset_raw,
+                    const float* d_opacity_raw, float shell_len, int resize_scale, float* d_means3D, float* d_scales,
+                    float* d_rotations, float* d_opacities, void* stream);
+int fs_pose_backward(int N, int V, int F, const float* d_verts, const long long* d_faces,
+                     const long long* d_face_index, const float* d_bary, const float* d_face_scale_canonical,
+                     const float* d_scaling_raw, const float* d_rotation_raw, const float* d_offset_raw,
+                     const float* d_opacity_raw, float shell_len, int resize_scale, const float* d_dL_dmeans3D,
+                     const float* d_dL_dscales, const float* d_dL_drotations, const float* d_dL_dopacities,
+                     float* d_dL_dverts, float* d_dL_dscaling_raw, float* d_dL_drotation_raw, float* d_dL_doffset_raw,
+                     float* d_dL_dopacity_raw, void* stream);
 
 /*
  * Optional per-stage device timing for bench.py's roofline figures.  While enabled, every stage launch is

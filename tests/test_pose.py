@@ -1,0 +1,104 @@
+"""Pose stage: oracle vs the reference's own mesh_compute.py, a property pin for the
+restated pytorch3d functions, and (GPU) the fused kernel vs the oracle forward + float64 autograd backward."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from fateavatar_b200 import scenes
+from oracle import pose_oracle as po
+
+REF_MESH = "/root/reference/volume_rendering/mesh_compute.py"
+
+
+def _t(a, dtype=torch.float64):
+    return torch.from_numpy(np.asarray(a)).to(dtype) if np.asarray(a).dtype.kind == "f" else torch.from_numpy(np.asarray(a))
+
+
+def oracle_run(p, dtype=torch.float64, grads=None):
+    verts = _t(p["verts"], dtype).requires_grad_(True)
+    leaves = [_t(p[k], dtype).requires_grad_(True) for k in ("scaling_raw", "rotation_raw", "offset_raw", "opacity_raw")]
+    faces, fi = torch.from_numpy(p["faces"]), torch.from_numpy(p["face_index"])
+    _, canon = po.compute_face_orientation(_t(p["canon_verts"], dtype), faces)
+    out = po.pose_splats(verts, faces, fi, _t(p["bary"], dtype), canon, *leaves, shell_len=p["shell_len"])
+    res = dict(out=[o.detach().numpy() for o in out], canon=canon.detach())
+    if grads is not None:
+        loss = sum((o * _t(g, dtype)).sum() for o, g in zip(out, grads))
+        loss.backward()
+        res["grads"] = [verts.grad.numpy()] + [l.grad.numpy() for l in leaves]
+    return res
+
+
+@pytest.mark.skipif(not os.path.exists(REF_MESH), reason="reference tree not mounted")
+def test_oracle_mesh_functions_match_reference_file():
+    spec = importlib.util.spec_from_file_location("ref_mesh_compute", REF_MESH)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    p = scenes.pose_inputs(N=10, seed=1)
+    verts, faces = torch.from_numpy(p["verts"])[None], torch.from_numpy(p["faces"])
+    o_ref, s_ref = ref.compute_face_orientation(verts, faces, return_scale=True)
+    o_me, s_me = po.compute_face_orientation(verts, faces)
+    assert torch.equal(o_ref, o_me) and torch.equal(s_ref, s_me)
+    assert torch.equal(ref.compute_face_normals(verts, faces), po.compute_face_normals(verts, faces))
+
+
+def test_restated_pytorch3d_quaternion_functions_properties():
+    """pytorch3d is not vendored (parity unpinned): pin the restatement by the mathematical contract instead."""
+    g = torch.Generator().manual_seed(0)
+    q = torch.nn.functional.normalize(torch.randn(2000, 4, generator=g, dtype=torch.float64), dim=-1)
+    r, x, y, z = q.unbind(-1)
+    M = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+                     2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                     2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], -1).reshape(-1, 3, 3)
+    q2 = po.matrix_to_quaternion(M)
+    assert torch.allclose(q2, po.standardize_quaternion(q), atol=1e-9)          # inverse of quaternion->matrix
+    a = torch.nn.functional.normalize(torch.randn(2000, 4, generator=g, dtype=torch.float64), dim=-1)
+    prod = po.quaternion_multiply(a, q)
+    assert (prod[:, 0] >= 0).all() and torch.allclose(prod.norm(dim=-1), torch.ones(2000, dtype=torch.float64))
+    ra, rq, rp = (po_matrix(t) for t in (a, q, prod))
+    assert torch.allclose(ra @ rq, rp, atol=1e-9)                               # composes rotations
+
+
+def po_matrix(q):
+    r, x, y, z = q.unbind(-1)
+    return torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - r * z), 2 * (x * z + r * y),
+                        2 * (x * y + r * z), 1 - 2 * (x * x + z * z), 2 * (y * z - r * x),
+                        2 * (x * z - r * y), 2 * (y * z + r * x), 1 - 2 * (x * x + y * y)], -1).reshape(-1, 3, 3)
+
+
+def test_pose_oracle_invariants():
+    p = scenes.pose_inputs(N=500, seed=2)
+    res = oracle_run(p)
+    xyz, sc, rot, op = res["out"]
+    assert xyz.shape == (500, 3) and np.allclose(np.linalg.norm(rot, axis=1), 1.0) and (rot[:, 0] >= 0).all()
+    assert (sc > 0).all() and ((op > 0) & (op < 1)).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [1, 1000, 100000])
+def test_pose_kernel_vs_oracle(N, cuda_device):
+    from fateavatar_b200 import pose
+
+    dev = cuda_device
+    p = scenes.pose_inputs(N=N, seed=3)
+    rng = np.random.default_rng(4)
+    gs = [rng.standard_normal(s).astype(np.float32) for s in ((N, 3), (N, 3), (N, 4), (N, 1))]
+    ref = oracle_run(p, grads=gs)
+    d = lambda k, req=False: torch.from_numpy(p[k]).to(dev).requires_grad_(req)
+    verts = d("verts", True)
+    leaves = [d(k, True) for k in ("scaling_raw", "rotation_raw", "offset_raw", "opacity_raw")]
+    out = pose.pose_splats(verts[None], d("faces"), d("face_index"), d("bary"), ref["canon"].float().to(dev), *leaves,
+                           shell_len=p["shell_len"])
+    # forward: fp32 kernel vs float64 oracle; tolerance 2e-5 relative to each tensor's max magnitude
+    for got, want, name in zip(out, ref["out"], ("means3D", "scales", "rotations", "opacities")):
+        err = np.abs(got.detach().cpu().numpy().astype(np.float64) - want).max()
+        assert err <= 2e-5 * max(np.abs(want).max(), 1e-12), (name, err)
+    loss = sum((o * torch.from_numpy(g).to(dev)).sum() for o, g in zip(out, gs))
+    loss.backward()
+    got_g = [verts.grad] + [l.grad for l in leaves]
+    for got, want, name in zip(got_g, ref["grads"], ("verts", "scaling", "rotation", "offset", "opacity")):
+        w = np.asarray(want, np.float64)
+        err = np.abs(got.cpu().numpy().astype(np.float64).reshape(w.shape) - w).max()
+        assert err <= 2e-4 * max(np.abs(w).max(), 1e-12), (name, err, np.abs(w).max())
