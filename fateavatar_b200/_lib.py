@@ -41,7 +41,7 @@ EXPORTS = [
 ]
 
 STAGES = ["preprocess", "tile_scan", "scatter", "tile_sort", "big_tile_sort", "blend_forward", "blend_backward",
-          "preprocess_backward", "knn"]
+          "preprocess_backward", "knn", "pose_forward", "pose_backward"]
 
 _lib = None
 

@@ -287,6 +287,7 @@ int fs_pose_forward(int N, int V, int F, const float* d_verts, const long long* 
         fs_set_error("fs_pose_forward: required pointer is NULL");
         return FS_ERR_INVALID_ARGUMENT;
     }
+    FsStageTimer timer(FS_STAGE_POSE_FWD, static_cast<cudaStream_t>(stream));
     pose_forward_kernel<<<(N + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         N, d_verts, d_faces, d_face_index, d_bary, d_face_scale_canonical, d_scaling_raw, d_rotation_raw, d_offset_raw,
         d_opacity_raw, shell_len, resize_scale, d_means3D, d_scales, d_rotations, d_opacities);
@@ -322,6 +323,7 @@ int fs_pose_backward(int N, int V, int F, const float* d_verts, const long long*
         fs_set_error("fs_pose_backward: required pointer is NULL");
         return FS_ERR_INVALID_ARGUMENT;
     }
+    FsStageTimer timer(FS_STAGE_POSE_BWD, st);
     pose_backward_kernel<<<(N + 255) / 256, 256, 0, st>>>(
         N, d_verts, d_faces, d_face_index, d_bary, d_face_scale_canonical, d_scaling_raw, d_rotation_raw, d_offset_raw,
         d_opacity_raw, shell_len, resize_scale, d_dL_dmeans3D, d_dL_dscales, d_dL_drotations, d_dL_dopacities,

@@ -22,6 +22,43 @@ from . import _lib
 from ._lib import FateSplatError
 
 
+def pose_forward_raw(verts, faces, face_index, bary, canon, scaling_raw, rotation_raw, offset_raw, opacity_raw,
+                     shell_len=0.05, resize_scale=True, out=None):
+    """One fs_pose_forward call on contiguous CUDA tensors (no autograd).  Returns (xyz, scales, rots, opac)."""
+    lib = _lib.load()
+    dev = verts.device
+    N, V, F = face_index.shape[0], verts.shape[-2], faces.shape[0]
+    xyz, scales, rots, opac = out if out is not None else (
+        torch.empty((N, 3), device=dev), torch.empty((N, 3), device=dev), torch.empty((N, 4), device=dev),
+        torch.empty((N, 1), device=dev))
+    rc = lib.fs_pose_forward(N, V, F, verts.data_ptr(), faces.data_ptr(), face_index.data_ptr(), bary.data_ptr(),
+                             canon.data_ptr(), scaling_raw.data_ptr(), rotation_raw.data_ptr(), offset_raw.data_ptr(),
+                             opacity_raw.data_ptr(), float(shell_len), int(bool(resize_scale)), xyz.data_ptr(),
+                             scales.data_ptr(), rots.data_ptr(), opac.data_ptr(),
+                             torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "fs_pose_forward")
+    return xyz, scales, rots, opac
+
+
+def pose_backward_raw(verts, faces, face_index, bary, canon, scaling_raw, rotation_raw, offset_raw, opacity_raw,
+                      g_xyz, g_scales, g_rots, g_opac, shell_len=0.05, resize_scale=True, out=None):
+    """One fs_pose_backward call.  Returns (d_verts, d_scaling, d_rotation, d_offset, d_opacity)."""
+    lib = _lib.load()
+    dev = verts.device
+    N, V, F = face_index.shape[0], verts.shape[-2], faces.shape[0]
+    d_verts, d_sr, d_rr, d_of, d_op = out if out is not None else (
+        torch.empty((V, 3), device=dev), torch.empty((N, 3), device=dev), torch.empty((N, 4), device=dev),
+        torch.empty((N, 1), device=dev), torch.empty((N, 1), device=dev))
+    rc = lib.fs_pose_backward(N, V, F, verts.data_ptr(), faces.data_ptr(), face_index.data_ptr(), bary.data_ptr(),
+                              canon.data_ptr(), scaling_raw.data_ptr(), rotation_raw.data_ptr(), offset_raw.data_ptr(),
+                              opacity_raw.data_ptr(), float(shell_len), int(bool(resize_scale)), g_xyz.data_ptr(),
+                              g_scales.data_ptr(), g_rots.data_ptr(), g_opac.data_ptr(), d_verts.data_ptr(),
+                              d_sr.data_ptr(), d_rr.data_ptr(), d_of.data_ptr(), d_op.data_ptr(),
+                              torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "fs_pose_backward")
+    return d_verts, d_sr, d_rr, d_of, d_op
+
+
 class _PoseSplats(torch.autograd.Function):
     @staticmethod
     def forward(ctx, verts, scaling_raw, rotation_raw, offset_raw, opacity_raw, faces, face_index, bary, canon,

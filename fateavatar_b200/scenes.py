@@ -186,7 +186,11 @@ def pose_inputs(N=100000, seed=0):
     canon_verts, faces = ellipsoid_mesh()
     bend = 0.08 * np.sin(6.0 * canon_verts[:, [1, 2, 0]]) * canon_verts + 0.002 * rng.standard_normal(canon_verts.shape)
     verts = (canon_verts + bend).astype(np.float32)
-    face_index = rng.integers(0, faces.shape[0], N).astype(np.int64)
+    # splat sites are spread uniformly over the surface (FateAvatar samples the template uniformly in UV space,
+    # volume_rendering/mesh_sampling.py:86-138): faces are drawn proportionally to their area
+    tri = canon_verts[faces]
+    area = 0.5 * np.linalg.norm(np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]), axis=1).astype(np.float64)
+    face_index = rng.choice(faces.shape[0], size=N, p=area / area.sum()).astype(np.int64)
     bary = rng.dirichlet(np.ones(3), N).astype(np.float32)
     return dict(
         verts=verts, canon_verts=canon_verts, faces=faces, face_index=face_index, bary=bary,

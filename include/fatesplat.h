@@ -149,9 +149,9 @@ int fs_pose_backward(int N, int V, int F, const float* d_verts, const long long*
  * Optional per-stage device timing for bench.py's roofline figures.  While enabled, every stage launch is
  * bracketed by CUDA events on the launching stream; fs_profile_read waits for them and returns, per stage id
  * (0 preprocess, 1 tile_scan, 2 scatter, 3 tile_sort, 4 big_tile_sort, 5 blend_forward, 6 blend_backward,
- * 7 preprocess_backward, 8 knn), the summed milliseconds and the number of launches since the last read.
+ * 7 preprocess_backward, 8 knn, 9 pose_forward, 10 pose_backward), the summed milliseconds and the number of launches since the last read.
  */
-#define FS_NUM_STAGES 9
+#define FS_NUM_STAGES 11
 void fs_profile_enable(int on);
 int fs_profile_read(float* total_ms, int* counts, int n);
 
