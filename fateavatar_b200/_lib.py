@@ -24,7 +24,7 @@ class FsFrameInfo(C.Structure):
 
 _LAYOUT_FIELDS = [
     "total_bytes", "info", "depths", "cov3D", "splat", "clamped", "rect", "tiles_touched", "tile_count",
-    "tile_cursor", "ranges", "big_tiles", "work_order", "inst_keys", "inst_keys_alt", "point_list", "inst_splat", "final_T",
+    "tile_cursor", "ranges", "big_tiles", "work_order", "seg_base", "seg_info", "ckpt", "final_C", "inst_keys", "inst_keys_alt", "point_list", "inst_splat", "final_T",
     "n_contrib", "bwd_counter", "grad_acc", "instance_capacity",
 ]
 

@@ -111,6 +111,11 @@ void fs_compute_layout(int P, int W, int H, size_t Rcap, fs_workspace_layout* L)
     L->ranges = take(Tn * 8);
     L->big_tiles = take((Tn + 1) * 4);
     L->work_order = take(Tn * 4);
+    const size_t Smax = Rcap / FS_SEG + Tn + 1;
+    L->seg_base = take((Tn + 1) * 4);
+    L->seg_info = take(Smax * 8);
+    L->ckpt = take(Smax * FS_TILE_PIX * 16);
+    L->final_C = take((size_t)W * H * 16);
     L->depths = take(Pn * 4);
     L->cov3D = take(Pn * 24);
     L->splat = take(Pn * 48);

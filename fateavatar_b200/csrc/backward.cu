@@ -59,10 +59,17 @@ struct WarpStage {
     SplatRec rec[2][kBatch];
 };
 
-// Persistent warps pull (tile, 8x4 block) units heaviest-first, exactly like the forward kernel.
+// Persistent warps pull (tile, depth segment, 8x4 block) units from an atomic work counter.  A depth segment is
+// FS_SEG consecutive positions of the tile's sorted list; the forward kernel left, for every pixel, the
+// transmittance and the colour accumulated behind each segment boundary (ckpt), so a unit can start its
+// back-to-front walk at its own segment instead of at the end of the list.  This bounds the serial chain of a
+// unit (the critical path when a dense tile's whole list belonged to one warp) and multiplies the number of
+// units available to keep every SM sub-partition busy.
 __global__ void __launch_bounds__(kWarps * 32)
-blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ work_order,
-                      const uint32_t* __restrict__ n_nonempty_tiles, uint32_t sm_count,
+blend_backward_kernel(const uint2* __restrict__ ranges, const uint2* __restrict__ seg_info,
+                      const uint32_t* __restrict__ seg_base, const float4* __restrict__ ckpt,
+                      const float4* __restrict__ final_C,
+                      const uint32_t* __restrict__ n_segments, uint32_t sm_count,
                       uint32_t* __restrict__ sm_slots, uint32_t* __restrict__ work_counter,
                       const SplatRec* __restrict__ inst_splat, int W, int H, const float* __restrict__ bg_color,
                       const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
@@ -73,7 +80,7 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     {   // keep ~2 dense units per active warp (see blend_forward.cu); surplus CTAs retire immediately
-        const uint32_t dense_units = __ldg(n_nonempty_tiles) * 8u;
+        const uint32_t dense_units = __ldg(n_segments) * 8u;
         const uint32_t want_per_sm = max(1u, dense_units / (2u * kWarps * sm_count));
         // placement-independent: the k-th CTA to arrive on an SM stays iff k < want_per_sm
         __shared__ uint32_t s_rank;
@@ -98,7 +105,7 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     const int gx = (W + FS_TILE - 1) / FS_TILE;
     const float bg0 = __ldg(bg_color), bg1 = __ldg(bg_color + 1), bg2 = __ldg(bg_color + 2);
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
-    const uint32_t n_units = __ldg(n_nonempty_tiles) * 8u;
+    const uint32_t n_units = __ldg(n_segments) * 8u;
     const size_t plane = (size_t)H * W;
 
     for (;;) {
@@ -106,7 +113,9 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         if (lane == 0) unit = atomicAdd(work_counter, 1u);
         unit = __shfl_sync(0xffffffffu, unit, 0);
         if (unit >= n_units) break;
-        const int tile = (int)work_order[unit >> 3];
+        const uint2 sg = seg_info[unit >> 3];
+        const int tile = (int)sg.x;
+        const uint32_t seg_lo = sg.y * FS_SEG;
         const int blk = (int)(unit & 7u);
         const int tile_x = tile % gx, tile_y = tile / gx;
         const int bx = tile_x * FS_TILE + (blk & 1) * 8, by = tile_y * FS_TILE + (blk >> 1) * 4;
@@ -129,15 +138,17 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         }
         const float bg_dot = bg0 * dpx + bg1 * dpy + bg2 * dpz;
 
-        // positions >= the block's largest n_contrib are never visited: the stream starts there
+        // this unit walks positions [seg_lo, seg_hi) back to front; positions >= the block's largest n_contrib
+        // are never visited, so the stream starts at min(seg_hi, that)
+        const uint32_t seg_hi = min(seg_lo + FS_SEG, range.y - range.x);
         uint32_t wl = last_contributor;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) wl = max(wl, __shfl_xor_sync(0xffffffffu, wl, o));
-        const uint32_t warp_last = min(wl, range.y - range.x);
-        const int nbatches = (int)((warp_last + kBatch - 1) / kBatch);
+        const uint32_t warp_last = min(wl, seg_hi);
+        const int nbatches = warp_last > seg_lo ? (int)((warp_last - seg_lo + kBatch - 1) / kBatch) : 0;
 
-        // batch k covers positions [lo_k, lo_k + cnt_k), walking down from warp_last
-        auto batch_lo = [&](int k) { return (uint32_t)max(0, (int)warp_last - (k + 1) * kBatch); };
+        // batch k covers positions [lo_k, lo_k + cnt_k), walking down from warp_last to seg_lo
+        auto batch_lo = [&](int k) { return (uint32_t)max((int)seg_lo, (int)warp_last - (k + 1) * kBatch); };
         auto batch_cnt = [&](int k) { return (warp_last - (uint32_t)k * kBatch) - batch_lo(k); };
         auto issue = [&](int k) {  // lane 0 only
             const uint32_t bytes = batch_cnt(k) * (uint32_t)sizeof(SplatRec);
@@ -151,6 +162,17 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         float ar0 = 0.f, ar1 = 0.f, ar2 = 0.f;  // accum_rec
         float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;  // last_color
         float last_alpha = 0.f;
+        if (last_contributor > seg_hi) {
+            // the pixel's list continues behind this segment: resume from the forward kernel's checkpoint
+            const float4 c4 = ckpt[((size_t)seg_base[tile] + sg.y + 1) * FS_TILE_PIX +
+                                   ((by - tile_y * FS_TILE) + (lane >> 3)) * FS_TILE + (bx - tile_x * FS_TILE) + (lane & 7)];
+            const float4 fc = final_C[pid];
+            const float inv = __fdividef(1.0f, c4.x);
+            T = c4.x;
+            ar0 = (fc.x - c4.y) * inv;  // colour accumulated behind the boundary
+            ar1 = (fc.y - c4.z) * inv;
+            ar2 = (fc.z - c4.w) * inv;
+        }
 
         for (int kb = 0; kb < nbatches; ++kb) {
             __syncwarp();
@@ -523,8 +545,9 @@ void fs_launch_backward(int P, int D, int M, const float* bg, int W, int H, cons
         const int ctas_per_sm = fs_tuning("FATESPLAT_BWD_CTAS_PER_SM", 2);  // upper bound (100 regs/thread)
         const int grid = fs_num_sms() * ctas_per_sm;
         blend_backward_kernel<<<grid, kWarps * 32, smem, stream>>>(
-            reinterpret_cast<const uint2*>(ws + L.ranges), reinterpret_cast<const uint32_t*>(ws + L.work_order),
-            &info->reserved[3], (uint32_t)fs_num_sms(), reinterpret_cast<uint32_t*>(ws + L.bwd_counter + 256),
+            reinterpret_cast<const uint2*>(ws + L.ranges), reinterpret_cast<const uint2*>(ws + L.seg_info),
+            reinterpret_cast<const uint32_t*>(ws + L.seg_base), reinterpret_cast<const float4*>(ws + L.ckpt),
+            reinterpret_cast<const float4*>(ws + L.final_C), &info->reserved[2], (uint32_t)fs_num_sms(), reinterpret_cast<uint32_t*>(ws + L.bwd_counter + 256),
             reinterpret_cast<uint32_t*>(ws + L.bwd_counter),
             reinterpret_cast<const SplatRec*>(ws + L.inst_splat), W, H, bg,
             reinterpret_cast<const float*>(ws + L.final_T), reinterpret_cast<const uint32_t*>(ws + L.n_contrib),

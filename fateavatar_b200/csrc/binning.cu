@@ -29,44 +29,65 @@ constexpr int kScanThreads = 1024;
 __global__ void __launch_bounds__(kScanThreads)
 tile_scan_kernel(int Tn, const uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_cursor,
                  uint2* __restrict__ ranges, uint32_t* __restrict__ big_tiles, uint32_t* __restrict__ work_order,
-                 fs_frame_info* __restrict__ info, uint32_t Rcap) {
+                 uint32_t* __restrict__ seg_base, uint2* __restrict__ seg_info, fs_frame_info* __restrict__ info,
+                 uint32_t Rcap) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_wmax[32];
     __shared__ uint32_t s_nbig;
     __shared__ uint32_t s_bin[33];  // tiles per log2(count) class; class 0 = empty
+    __shared__ uint32_t s_wseg[32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) s_nbig = 0;
     if (tid < 33) s_bin[tid] = 0;
     __syncthreads();
     const int per = (Tn + kScanThreads - 1) / kScanThreads;
     const int beg = min(Tn, tid * per), end = min(Tn, beg + per);
-    uint32_t sum = 0, mx = 0;
+    uint32_t sum = 0, mx = 0, segs = 0;
     for (int t = beg; t < end; ++t) {
         const uint32_t c = tile_count[(size_t)t * FS_CNT_STRIDE];
         sum += c;
+        segs += (c + FS_SEG - 1) / FS_SEG;
         mx = max(mx, c);
         atomicAdd(&s_bin[c ? 32 - __clz(c) : 0], 1u);
     }
-    uint32_t incl = sum;
+    uint32_t incl = sum, sincl = segs;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
+        const uint32_t w = __shfl_up_sync(0xffffffffu, sincl, o);
+        if (lane >= o) {
+            incl += v;
+            sincl += w;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 31) s_warp[wid] = incl;
+    if (lane == 31) {
+        s_warp[wid] = incl;
+        s_wseg[wid] = sincl;
+    }
     if (lane == 0) s_wmax[wid] = mx;
     __syncthreads();
     if (wid == 0) {
         uint32_t w = s_warp[lane];
         uint32_t wi = w;
+        uint32_t ws_ = s_wseg[lane];
+        uint32_t wsi = ws_;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
-            if (lane >= o) wi += v;
+            const uint32_t v2 = __shfl_up_sync(0xffffffffu, wsi, o);
+            if (lane >= o) {
+                wi += v;
+                wsi += v2;
+            }
         }
         s_warp[lane] = wi - w;  // exclusive prefix of warp totals
+        s_wseg[lane] = wsi - ws_;
+        if (lane == 31) {
+            info->reserved[2] = wsi;  // depth segments in this frame (work units of the backward blend / 8)
+            seg_base[Tn] = wsi;
+        }
         uint32_t m = s_wmax[lane];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -78,8 +99,13 @@ tile_scan_kernel(int Tn, const uint32_t* __restrict__ tile_count, uint32_t* __re
     }
     __syncthreads();
     uint32_t off = s_warp[wid] + (incl - sum);
+    uint32_t soff = s_wseg[wid] + (sincl - segs);
     for (int t = beg; t < end; ++t) {
         const uint32_t c = tile_count[(size_t)t * FS_CNT_STRIDE];
+        seg_base[t] = soff;
+        if (off + c <= Rcap)  // an overflowed frame never reads these
+            for (uint32_t k = 0; k < (c + FS_SEG - 1) / FS_SEG; ++k) seg_info[soff + k] = make_uint2((uint32_t)t, k);
+        soff += (c + FS_SEG - 1) / FS_SEG;
         tile_cursor[(size_t)t * FS_CNT_STRIDE] = off;
         ranges[t] = c ? make_uint2(off, off + c) : make_uint2(0u, 0u);  // empty tiles stay (0,0) like the memset
         if (c > FS_SORT_SMEM_CAP) big_tiles[1 + atomicAdd(&s_nbig, 1u)] = (uint32_t)t;
@@ -354,14 +380,16 @@ void fs_launch_binning(int P, int W, int H, char* ws, const fs_workspace_layout&
     auto* ranges = reinterpret_cast<uint2*>(ws + L.ranges);
     auto* big = reinterpret_cast<uint32_t*>(ws + L.big_tiles);
     auto* work_order = reinterpret_cast<uint32_t*>(ws + L.work_order);
+    auto* seg_base = reinterpret_cast<uint32_t*>(ws + L.seg_base);
+    auto* seg_info = reinterpret_cast<uint2*>(ws + L.seg_info);
     auto* keys = reinterpret_cast<u64*>(ws + L.inst_keys);
     auto* splat = reinterpret_cast<const float4*>(ws + L.splat);
     auto* point_list = reinterpret_cast<uint32_t*>(ws + L.point_list);
     auto* inst_splat = reinterpret_cast<float4*>(ws + L.inst_splat);
     {
         FsStageTimer t(FS_STAGE_TILE_SCAN, stream);
-        tile_scan_kernel<<<1, kScanThreads, 0, stream>>>(Tn, tile_count, tile_cursor, ranges, big, work_order, info,
-                                                         Rcap);
+        tile_scan_kernel<<<1, kScanThreads, 0, stream>>>(Tn, tile_count, tile_cursor, ranges, big, work_order, seg_base,
+                                                         seg_info, info, Rcap);
     }
     {
         FsStageTimer t(FS_STAGE_SCATTER, stream);

@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(kWarps * 32)
 blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ work_order, int n_tiles,
                      const uint32_t* __restrict__ n_nonempty_tiles, uint32_t sm_count,
                      uint32_t* __restrict__ sm_slots, uint32_t* __restrict__ work_counter, const SplatRec* __restrict__ inst_splat, int W, int H,
+                     const uint32_t* __restrict__ seg_base, float4* __restrict__ ckpt, float4* __restrict__ final_C,
                      const float* __restrict__ bg_color, float* __restrict__ out_color, float* __restrict__ final_T,
                      uint32_t* __restrict__ n_contrib, uint32_t Rcap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -163,9 +164,15 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
         uint32_t last_contributor = 0;
         bool done = !inside;
         bool warp_done = __all_sync(0xffffffffu, done);
+        // checkpoints for the backward blend: per-pixel (T, C) before list positions k*FS_SEG, k = 1, 2, ...
+        float4* ck = ckpt + (size_t)seg_base[tile] * FS_TILE_PIX + ((by - tile_y * FS_TILE) + (lane >> 3)) * FS_TILE +
+                     (bx - tile_x * FS_TILE) + (lane & 7);
 
         int b = 0;
         for (; b < nbatches; ++b) {
+            if (b > 0 && (b * kBatch) % FS_SEG == 0) {
+                ck[(size_t)(b * kBatch / FS_SEG) * FS_TILE_PIX] = make_float4(T, C0, C1, C2);
+            }
             __syncwarp();  // every lane is done reading the stage that batch b+1 will overwrite
             if (lane == 0 && b + 1 < nbatches) issue(b + 1);
             const uint32_t f = fills + (uint32_t)b;
@@ -210,6 +217,7 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
         if (inside) {
             const size_t pid = (size_t)py * W + px;
             final_T[pid] = T;
+            final_C[pid] = make_float4(C0, C1, C2, 0.0f);
             n_contrib[pid] = last_contributor;
             const size_t plane = (size_t)H * W;
             out_color[pid] = fs::mad(bg0, T, C0);
@@ -236,7 +244,9 @@ void fs_launch_blend_forward(int W, int H, const float* bg, float* out_color, ch
     const int grid = fs_num_sms() * ctas_per_sm;
     blend_forward_kernel<<<grid, kWarps * 32, smem, stream>>>(
         reinterpret_cast<const uint2*>(ws + L.ranges), reinterpret_cast<const uint32_t*>(ws + L.work_order), gx * gy,
-        &info->reserved[3], (uint32_t)fs_num_sms(), reinterpret_cast<uint32_t*>(info + 1), &info->reserved[1], reinterpret_cast<const SplatRec*>(ws + L.inst_splat), W, H, bg, out_color,
+        &info->reserved[3], (uint32_t)fs_num_sms(), reinterpret_cast<uint32_t*>(info + 1), &info->reserved[1], reinterpret_cast<const SplatRec*>(ws + L.inst_splat), W, H,
+        reinterpret_cast<const uint32_t*>(ws + L.seg_base), reinterpret_cast<float4*>(ws + L.ckpt),
+        reinterpret_cast<float4*>(ws + L.final_C), bg, out_color,
         reinterpret_cast<float*>(ws + L.final_T), reinterpret_cast<uint32_t*>(ws + L.n_contrib),
         (uint32_t)L.instance_capacity);
     fs_count_launch(1);

@@ -50,7 +50,7 @@ typedef struct fs_frame_info {
     uint32_t overflow;     /* 1 if R exceeded the workspace's instance capacity (frame is incomplete)       */
     uint32_t num_visible;  /* Gaussians with radii > 0                                                      */
     uint32_t max_tile_instances; /* heaviest tile's instance count                                         */
-    uint32_t reserved[4];  /* [0] prefiltered-violation flag, [1] forward work counter, [3] non-empty tiles */
+    uint32_t reserved[4];  /* [0] prefiltered-violation flag, [1] forward work counter, [2] depth segments, [3] non-empty tiles */
 } fs_frame_info;
 
 /* Byte offsets (from the workspace base) of the named per-frame arrays: the parity taps.
@@ -69,6 +69,12 @@ typedef struct fs_workspace_layout {
     size_t ranges;        /* uint32 [Tn][2]  (start,end) into point_list; (0,0) if empty     */
     size_t big_tiles;     /* uint32 [Tn+1]   [0]=count, then ids of tiles too large for the smem sort */
     size_t work_order;    /* uint32 [Tn]     tile ids, heaviest first (work list of the blend kernels) */
+    size_t seg_base;      /* uint32 [Tn+1]   first depth-segment id of every tile (segments of 256 list positions) */
+    size_t seg_info;      /* uint32 [Smax][2] (tile, segment index inside the tile), Smax = Rcap/256 + Tn + 1 */
+    size_t ckpt;          /* float4 [Smax][256] per-pixel (T, accumulated colour) before each segment boundary:
+                             lets the backward blend start in the middle of a tile's list */
+    size_t final_C;       /* float4 [H*W]    accumulated colour without background (backward: colour behind a
+                             boundary = (final_C - ckpt.C) / ckpt.T) */
     size_t inst_keys;     /* uint64 [Rcap]   (depth_bits<<32 | gaussian) per tile segment    */
     size_t inst_keys_alt; /* uint64 [Rcap]   ping-pong for the large-tile global sort        */
     size_t point_list;    /* uint32 [Rcap]   sorted Gaussian ids (== reference point_list)   */
