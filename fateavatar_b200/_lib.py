@@ -24,7 +24,7 @@ class FsFrameInfo(C.Structure):
 
 _LAYOUT_FIELDS = [
     "total_bytes", "info", "depths", "cov3D", "splat", "clamped", "rect", "tiles_touched", "tile_count",
-    "tile_cursor", "ranges", "big_tiles", "work_order", "seg_base", "seg_info", "ckpt", "final_C", "inst_keys", "inst_keys_alt", "point_list", "inst_splat", "final_T",
+    "tile_cursor", "ranges", "big_tiles", "work_order", "tile_meta", "seg_base", "seg_info", "ckpt", "final_C", "inst_keys", "inst_keys_alt", "point_list", "inst_splat", "final_T",
     "n_contrib", "bwd_counter", "grad_acc", "instance_capacity",
 ]
 
@@ -37,7 +37,7 @@ class FsWorkspaceLayout(C.Structure):
 EXPORTS = [
     "fs_workspace_bytes", "fs_get_workspace_layout", "fs_forward", "fs_backward", "fs_mark_visible",
     "fs_knn_workspace_bytes", "fs_knn_mean_dist2", "fs_last_launch_count", "fs_last_error", "fs_version",
-    "fs_profile_enable", "fs_profile_read", "fs_pose_forward", "fs_pose_backward",
+    "fs_profile_enable", "fs_profile_read", "fs_pose_forward", "fs_pose_backward", "fs_set_tile_hint",
 ]
 
 STAGES = ["preprocess", "tile_scan", "scatter", "tile_sort", "big_tile_sort", "blend_forward", "blend_backward",
@@ -82,6 +82,8 @@ def load():
     lib.fs_pose_forward.argtypes = [i, i, i] + [vp] * 9 + [f, i] + [vp] * 4 + [vp]
     lib.fs_pose_backward.restype = i
     lib.fs_pose_backward.argtypes = [i, i, i] + [vp] * 9 + [f, i] + [vp] * 4 + [vp] * 5 + [vp]
+    lib.fs_set_tile_hint.restype = None
+    lib.fs_set_tile_hint.argtypes = [C.c_uint32]
     lib.fs_profile_enable.restype = None
     lib.fs_profile_enable.argtypes = [i]
     lib.fs_profile_read.restype = i

@@ -28,6 +28,8 @@ int fs_launch_knn(int P, const float* points, float* out, char* ws, size_t ws_by
 
 static thread_local char g_err[512] = "";
 static thread_local int g_launches = 0;
+static thread_local uint32_t g_tile_hint = 0;
+uint32_t fs_tile_hint() { return g_tile_hint; }
 
 void fs_set_error(const char* fmt, ...) {
     va_list ap;
@@ -112,6 +114,7 @@ void fs_compute_layout(int P, int W, int H, size_t Rcap, fs_workspace_layout* L)
     L->big_tiles = take((Tn + 1) * 4);
     L->work_order = take(Tn * 4);
     const size_t Smax = Rcap / FS_SEG + Tn + 1;
+    L->tile_meta = take(Tn * 16);
     L->seg_base = take((Tn + 1) * 4);
     L->seg_info = take(Smax * 8);
     L->ckpt = take(Smax * FS_TILE_PIX * 16);
@@ -293,6 +296,8 @@ int fs_knn_mean_dist2(int P, const float* d_points, float* d_mean_dist2, void* d
     FS_CUDA_CHECK(cudaGetLastError());
     return FS_OK;
 }
+
+void fs_set_tile_hint(uint32_t max_tile_instances) { g_tile_hint = max_tile_instances; }
 
 void fs_profile_enable(int on) { g_prof_on = on != 0; }
 

@@ -66,8 +66,8 @@ struct WarpStage {
 // unit (the critical path when a dense tile's whole list belonged to one warp) and multiplies the number of
 // units available to keep every SM sub-partition busy.
 __global__ void __launch_bounds__(kWarps * 32)
-blend_backward_kernel(const uint2* __restrict__ ranges, const uint2* __restrict__ seg_info,
-                      const uint32_t* __restrict__ seg_base, const float4* __restrict__ ckpt,
+blend_backward_kernel(const uint4* __restrict__ tile_meta, const uint2* __restrict__ seg_info,
+                      const float4* __restrict__ ckpt,
                       const float4* __restrict__ final_C,
                       const uint32_t* __restrict__ n_segments, uint32_t sm_count,
                       uint32_t* __restrict__ sm_slots, uint32_t* __restrict__ work_counter,
@@ -78,6 +78,7 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint2* __restrict_
     WarpStage* stages = reinterpret_cast<WarpStage*>(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sizeof(WarpStage) * kWarps);
 
+    fs::pdl_trigger();  // the per-Gaussian kernel may begin launching; it waits for this grid before reading
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     {   // keep ~2 dense units per active warp (see blend_forward.cu); surplus CTAs retire immediately
         const uint32_t dense_units = __ldg(n_segments) * 8u;
@@ -124,7 +125,8 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint2* __restrict_
         const float pxf = (float)px, pyf = (float)py;
         const float wx0 = (float)bx, wx1 = (float)min(bx + 7, W - 1), wy0 = (float)by, wy1 = (float)min(by + 3, H - 1);
 
-        uint2 range = ranges[tile];
+        const uint4 meta = tile_meta[tile];
+        uint2 range = make_uint2(meta.x, meta.y);
         if (range.y > Rcap) range = make_uint2(0u, 0u);
 
         const size_t pid = (size_t)py * W + px;
@@ -164,7 +166,7 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint2* __restrict_
         float last_alpha = 0.f;
         if (last_contributor > seg_hi) {
             // the pixel's list continues behind this segment: resume from the forward kernel's checkpoint
-            const float4 c4 = ckpt[((size_t)seg_base[tile] + sg.y + 1) * FS_TILE_PIX +
+            const float4 c4 = ckpt[((size_t)meta.z + sg.y + 1) * FS_TILE_PIX +
                                    ((by - tile_y * FS_TILE) + (lane >> 3)) * FS_TILE + (bx - tile_x * FS_TILE) + (lane & 7)];
             const float4 fc = final_C[pid];
             const float inv = __fdividef(1.0f, c4.x);
@@ -315,6 +317,7 @@ preprocess_backward_kernel(int P, int D, int M, const float* __restrict__ means3
                            float* __restrict__ dL_dcolors, float* __restrict__ dL_dmeans3D,
                            float* __restrict__ dL_dcov3D, float* __restrict__ dL_dsh, float* __restrict__ dL_dscales,
                            float* __restrict__ dL_drots) {
+    fs::pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     float dcov[6] = {0, 0, 0, 0, 0, 0};
@@ -529,7 +532,6 @@ void fs_launch_backward(int P, int D, int M, const float* bg, int W, int H, cons
                         const int* radii, char* ws, const fs_workspace_layout& L, const float* dL_dpix,
                         float* dL_dmean2D, float* dL_dopacity, float* dL_dcolors, float* dL_dmean3D, float* dL_dcov3D,
                         float* dL_dsh, float* dL_dscale, float* dL_drot, cudaStream_t stream) {
-    const int gx = (W + FS_TILE - 1) / FS_TILE, gy = (H + FS_TILE - 1) / FS_TILE;
     float* grad_acc = reinterpret_cast<float*>(ws + L.grad_acc);
     // work counter (256-byte slot) and the per-Gaussian accumulator are contiguous: one memset node
     cudaMemsetAsync(ws + L.bwd_counter, 0, (L.grad_acc - L.bwd_counter) + (size_t)P * 48, stream);
@@ -545,8 +547,8 @@ void fs_launch_backward(int P, int D, int M, const float* bg, int W, int H, cons
         const int ctas_per_sm = fs_tuning("FATESPLAT_BWD_CTAS_PER_SM", 2);  // upper bound (100 regs/thread)
         const int grid = fs_num_sms() * ctas_per_sm;
         blend_backward_kernel<<<grid, kWarps * 32, smem, stream>>>(
-            reinterpret_cast<const uint2*>(ws + L.ranges), reinterpret_cast<const uint2*>(ws + L.seg_info),
-            reinterpret_cast<const uint32_t*>(ws + L.seg_base), reinterpret_cast<const float4*>(ws + L.ckpt),
+            reinterpret_cast<const uint4*>(ws + L.tile_meta), reinterpret_cast<const uint2*>(ws + L.seg_info),
+            reinterpret_cast<const float4*>(ws + L.ckpt),
             reinterpret_cast<const float4*>(ws + L.final_C), &info->reserved[2], (uint32_t)fs_num_sms(), reinterpret_cast<uint32_t*>(ws + L.bwd_counter + 256),
             reinterpret_cast<uint32_t*>(ws + L.bwd_counter),
             reinterpret_cast<const SplatRec*>(ws + L.inst_splat), W, H, bg,
@@ -558,7 +560,7 @@ void fs_launch_backward(int P, int D, int M, const float* bg, int W, int H, cons
     const float* cov = cov3D_precomp ? cov3D_precomp : reinterpret_cast<const float*>(ws + L.cov3D);
     const float* sh_in = colors_precomp ? nullptr : shs;
     FsStageTimer timer(FS_STAGE_PREPROCESS_BWD, stream);
-    preprocess_backward_kernel<<<(P + 255) / 256, 256, 0, stream>>>(
+    fs_launch_pdl(preprocess_backward_kernel, dim3((P + 255) / 256), dim3(256), 0, stream,
         P, D, M, means3D, radii, sh_in, reinterpret_cast<const uchar4*>(ws + L.clamped),
         cov3D_precomp ? nullptr : scales, rotations, scale_modifier, cov, viewmatrix, projmatrix, W, H, tan_fovx,
         tan_fovy, h_x, h_y, cam_pos, grad_acc, dL_dmean2D, dL_dopacity, dL_dcolors, dL_dmean3D, dL_dcov3D, dL_dsh,

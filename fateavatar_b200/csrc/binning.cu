@@ -29,13 +29,15 @@ constexpr int kScanThreads = 1024;
 __global__ void __launch_bounds__(kScanThreads)
 tile_scan_kernel(int Tn, const uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_cursor,
                  uint2* __restrict__ ranges, uint32_t* __restrict__ big_tiles, uint32_t* __restrict__ work_order,
-                 uint32_t* __restrict__ seg_base, uint2* __restrict__ seg_info, fs_frame_info* __restrict__ info,
-                 uint32_t Rcap) {
+                 uint32_t* __restrict__ seg_base, uint2* __restrict__ seg_info, uint4* __restrict__ tile_meta,
+                 fs_frame_info* __restrict__ info, uint32_t Rcap) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_wmax[32];
     __shared__ uint32_t s_nbig;
     __shared__ uint32_t s_bin[33];  // tiles per log2(count) class; class 0 = empty
     __shared__ uint32_t s_wseg[32];
+    fs::pdl_trigger();
+    fs::pdl_wait();
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) s_nbig = 0;
     if (tid < 33) s_bin[tid] = 0;
@@ -108,6 +110,7 @@ tile_scan_kernel(int Tn, const uint32_t* __restrict__ tile_count, uint32_t* __re
         soff += (c + FS_SEG - 1) / FS_SEG;
         tile_cursor[(size_t)t * FS_CNT_STRIDE] = off;
         ranges[t] = c ? make_uint2(off, off + c) : make_uint2(0u, 0u);  // empty tiles stay (0,0) like the memset
+        tile_meta[t] = c ? make_uint4(off, off + c, seg_base[t], 0u) : make_uint4(0u, 0u, 0u, 0u);
         if (c > FS_SORT_SMEM_CAP) big_tiles[1 + atomicAdd(&s_nbig, 1u)] = (uint32_t)t;
         off += c;
     }
@@ -133,6 +136,8 @@ tile_scan_kernel(int Tn, const uint32_t* __restrict__ tile_count, uint32_t* __re
 __global__ void __launch_bounds__(256)
 scatter_kernel(int P, int gx, const ushort4* __restrict__ rect, const float* __restrict__ depths,
                uint32_t* __restrict__ tile_cursor, u64* __restrict__ keys, uint32_t Rcap) {
+    fs::pdl_trigger();
+    fs::pdl_wait();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P) return;
     const ushort4 rc = rect[idx];
@@ -317,15 +322,27 @@ __device__ __forceinline__ void emit_sorted(const u64* keys, uint32_t n, uint32_
 constexpr int kSortThreads = 256;
 constexpr int kSortPer = FS_SORT_SMEM_CAP / kSortThreads;
 __global__ void __launch_bounds__(kSortThreads)
-tile_sort_kernel(const uint2* __restrict__ ranges, const u64* __restrict__ keys, const float4* __restrict__ splat,
-                 uint32_t* __restrict__ point_list, float4* __restrict__ inst_splat, uint32_t Rcap) {
+tile_sort_kernel(const uint2* __restrict__ ranges, u64* __restrict__ keys, const float4* __restrict__ splat,
+                 uint32_t* __restrict__ point_list, float4* __restrict__ inst_splat, uint32_t Rcap,
+                 int big_kernel_follows) {
     __shared__ u64 s_grp[FS_SORT_SMEM_CAP];
     __shared__ u64 s_out[FS_SORT_SMEM_CAP];
     __shared__ uint32_t s_cnt[FS_SORT_SMEM_CAP + 1];
     __shared__ uint32_t s_red[2 * (kSortThreads / 32)];
+    fs::pdl_trigger();
+    fs::pdl_wait();
     const uint2 r = ranges[blockIdx.x];
     const uint32_t n = r.y - r.x;
-    if (n == 0 || n > FS_SORT_SMEM_CAP || r.y > Rcap) return;
+    if (n == 0 || r.y > Rcap) return;
+    if (n > FS_SORT_SMEM_CAP) {
+        // oversized tile: normally left to big_tile_sort_kernel; when the caller's hint said no tile would be
+        // this large and that launch was skipped, sort it here in global memory (slow, but always correct)
+        if (!big_kernel_follows) {
+            bitonic_sort_ascending(keys + r.x, n, threadIdx.x, kSortThreads);
+            emit_sorted(keys + r.x, n, r.x, splat, point_list, inst_splat, threadIdx.x, kSortThreads);
+        }
+        return;
+    }
     bucket_sort<kSortThreads, kSortPer, FS_SORT_SMEM_CAP>(keys + r.x, n, s_grp, s_out, s_cnt, s_red);
     emit_sorted(s_out, n, r.x, splat, point_list, inst_splat, threadIdx.x, kSortThreads);
 }
@@ -343,6 +360,8 @@ big_tile_sort_kernel(const uint32_t* __restrict__ big_tiles, const uint2* __rest
                      float4* __restrict__ inst_splat, uint32_t Rcap) {
     extern __shared__ __align__(16) u64 d_smem[];
     __shared__ uint32_t s_red[2 * (kBigThreads / 32)];
+    fs::pdl_trigger();
+    fs::pdl_wait();
     const uint32_t nbig = big_tiles[0];
     for (uint32_t b = blockIdx.x; b < nbig; b += gridDim.x) {
         const uint2 r = ranges[big_tiles[1 + b]];
@@ -382,24 +401,35 @@ void fs_launch_binning(int P, int W, int H, char* ws, const fs_workspace_layout&
     auto* work_order = reinterpret_cast<uint32_t*>(ws + L.work_order);
     auto* seg_base = reinterpret_cast<uint32_t*>(ws + L.seg_base);
     auto* seg_info = reinterpret_cast<uint2*>(ws + L.seg_info);
+    auto* tile_meta = reinterpret_cast<uint4*>(ws + L.tile_meta);
     auto* keys = reinterpret_cast<u64*>(ws + L.inst_keys);
     auto* splat = reinterpret_cast<const float4*>(ws + L.splat);
     auto* point_list = reinterpret_cast<uint32_t*>(ws + L.point_list);
     auto* inst_splat = reinterpret_cast<float4*>(ws + L.inst_splat);
+    // The oversized-tile kernel costs ~6 us of pure launch latency; skip it when the caller's hint (heaviest tile
+    // of recent frames, fs_set_tile_hint) says no tile comes near the in-kernel capacity.  A wrong hint only
+    // costs speed: tile_sort_kernel then sorts such a tile itself in global memory.
+    const uint32_t hint = fs_tile_hint();
+    const bool launch_big = hint == 0 || hint > (FS_SORT_SMEM_CAP * 3) / 4;
     {
         FsStageTimer t(FS_STAGE_TILE_SCAN, stream);
-        tile_scan_kernel<<<1, kScanThreads, 0, stream>>>(Tn, tile_count, tile_cursor, ranges, big, work_order, seg_base,
-                                                         seg_info, info, Rcap);
+        fs_launch_pdl(tile_scan_kernel, dim3(1), dim3(kScanThreads), 0, stream, Tn, tile_count, tile_cursor, ranges, big,
+                      work_order, seg_base, seg_info, tile_meta, info, Rcap);
     }
     {
         FsStageTimer t(FS_STAGE_SCATTER, stream);
-        scatter_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, gx, reinterpret_cast<const ushort4*>(ws + L.rect),
-                                                            reinterpret_cast<const float*>(ws + L.depths),
-                                                            tile_cursor, keys, Rcap);
+        fs_launch_pdl(scatter_kernel, dim3((P + 255) / 256), dim3(256), 0, stream, P, gx,
+                      reinterpret_cast<const ushort4*>(ws + L.rect), reinterpret_cast<const float*>(ws + L.depths),
+                      tile_cursor, keys, Rcap);
     }
     {
         FsStageTimer t(FS_STAGE_TILE_SORT, stream);
-        tile_sort_kernel<<<Tn, kSortThreads, 0, stream>>>(ranges, keys, splat, point_list, inst_splat, Rcap);
+        fs_launch_pdl(tile_sort_kernel, dim3(Tn), dim3(kSortThreads), 0, stream, ranges, keys, splat, point_list,
+                      inst_splat, Rcap, launch_big ? 1 : 0);
+    }
+    if (!launch_big) {
+        fs_count_launch(3);
+        return;
     }
     static bool attr_set = false;
     if (!attr_set) {
@@ -408,8 +438,8 @@ void fs_launch_binning(int P, int W, int H, char* ws, const fs_workspace_layout&
     }
     {
         FsStageTimer t(FS_STAGE_BIG_TILE_SORT, stream);
-        big_tile_sort_kernel<<<64, kBigThreads, kBigSmemBytes, stream>>>(big, ranges, keys, splat, point_list,
-                                                                        inst_splat, Rcap);
+        fs_launch_pdl(big_tile_sort_kernel, dim3(64), dim3(kBigThreads), kBigSmemBytes, stream, big, ranges, keys, splat,
+                      point_list, inst_splat, Rcap);
     }
     fs_count_launch(4);
 }

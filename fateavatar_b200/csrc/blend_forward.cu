@@ -39,7 +39,6 @@ struct Group {
     int jj[kGroup];
     bool any;
 };
-__device__ __forceinline__ bool cur_valid(const Group& g) { return g.any; }
 
 // extract the next (up to) four set bits of m and evaluate alpha for this lane's pixel
 __device__ __forceinline__ void compute_group(Group& g, unsigned& m, int c, const SplatRec* __restrict__ rec, float pxf,
@@ -91,16 +90,17 @@ __device__ __forceinline__ void apply_group(const Group& g, uint32_t base, float
 }
 
 __global__ void __launch_bounds__(kWarps * 32)
-blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ work_order, int n_tiles,
+blend_forward_kernel(const uint4* __restrict__ tile_meta, const uint32_t* __restrict__ work_order, int n_tiles,
                      const uint32_t* __restrict__ n_nonempty_tiles, uint32_t sm_count,
                      uint32_t* __restrict__ sm_slots, uint32_t* __restrict__ work_counter, const SplatRec* __restrict__ inst_splat, int W, int H,
-                     const uint32_t* __restrict__ seg_base, float4* __restrict__ ckpt, float4* __restrict__ final_C,
+                     float4* __restrict__ ckpt, float4* __restrict__ final_C,
                      const float* __restrict__ bg_color, float* __restrict__ out_color, float* __restrict__ final_T,
                      uint32_t* __restrict__ n_contrib, uint32_t Rcap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     WarpStage* stages = reinterpret_cast<WarpStage*>(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sizeof(WarpStage) * kWarps);
 
+    fs::pdl_wait();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     // Dynamic balancing needs clearly more heavy units than warps (a warp that owns a single dense unit is
     // the critical path), so only as many CTAs stay active as there are ~2 dense units per warp; the launch
@@ -146,7 +146,8 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
         const float pxf = (float)px, pyf = (float)py;
         const float wx0 = (float)bx, wx1 = (float)min(bx + 7, W - 1), wy0 = (float)by, wy1 = (float)min(by + 3, H - 1);
 
-        uint2 range = ranges[tile];
+        const uint4 meta = tile_meta[tile];  // range and first checkpoint slot in one 16-byte load
+        uint2 range = make_uint2(meta.x, meta.y);
         if (range.y > Rcap) range = make_uint2(0u, 0u);  // overflowed frame: flagged in the header, stay in bounds
         const uint32_t total = range.y - range.x;
         const int nbatches = (int)((total + kBatch - 1) / kBatch);
@@ -165,16 +166,16 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
         bool done = !inside;
         bool warp_done = __all_sync(0xffffffffu, done);
         // checkpoints for the backward blend: per-pixel (T, C) before list positions k*FS_SEG, k = 1, 2, ...
-        float4* ck = ckpt + (size_t)seg_base[tile] * FS_TILE_PIX + ((by - tile_y * FS_TILE) + (lane >> 3)) * FS_TILE +
+        float4* ck = ckpt + (size_t)meta.z * FS_TILE_PIX + ((by - tile_y * FS_TILE) + (lane >> 3)) * FS_TILE +
                      (bx - tile_x * FS_TILE) + (lane & 7);
 
         int b = 0;
         for (; b < nbatches; ++b) {
+            __syncwarp();  // every lane is done reading the stage that batch b+1 will overwrite
+            if (lane == 0 && b + 1 < nbatches) issue(b + 1);
             if (b > 0 && (b * kBatch) % FS_SEG == 0) {
                 ck[(size_t)(b * kBatch / FS_SEG) * FS_TILE_PIX] = make_float4(T, C0, C1, C2);
             }
-            __syncwarp();  // every lane is done reading the stage that batch b+1 will overwrite
-            if (lane == 0 && b + 1 < nbatches) issue(b + 1);
             const uint32_t f = fills + (uint32_t)b;
             fs::mbar_wait(&s_full[f & 1u], (f >> 1) & 1u);
             const SplatRec* rec = rec_ring[f & 1u];
@@ -242,10 +243,10 @@ void fs_launch_blend_forward(int W, int H, const float* bg, float* out_color, ch
     auto* info = reinterpret_cast<fs_frame_info*>(ws + L.info);
     const int ctas_per_sm = fs_tuning("FATESPLAT_FWD_CTAS_PER_SM", 4);  // upper bound; see the kernel prologue
     const int grid = fs_num_sms() * ctas_per_sm;
-    blend_forward_kernel<<<grid, kWarps * 32, smem, stream>>>(
-        reinterpret_cast<const uint2*>(ws + L.ranges), reinterpret_cast<const uint32_t*>(ws + L.work_order), gx * gy,
+    fs_launch_pdl(blend_forward_kernel, dim3(grid), dim3(kWarps * 32), smem, stream,
+        reinterpret_cast<const uint4*>(ws + L.tile_meta), reinterpret_cast<const uint32_t*>(ws + L.work_order), gx * gy,
         &info->reserved[3], (uint32_t)fs_num_sms(), reinterpret_cast<uint32_t*>(info + 1), &info->reserved[1], reinterpret_cast<const SplatRec*>(ws + L.inst_splat), W, H,
-        reinterpret_cast<const uint32_t*>(ws + L.seg_base), reinterpret_cast<float4*>(ws + L.ckpt),
+        reinterpret_cast<float4*>(ws + L.ckpt),
         reinterpret_cast<float4*>(ws + L.final_C), bg, out_color,
         reinterpret_cast<float*>(ws + L.final_T), reinterpret_cast<uint32_t*>(ws + L.n_contrib),
         (uint32_t)L.instance_capacity);

@@ -153,6 +153,12 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  : "memory");
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with fs_launch_pdl may start while its predecessor in
+// the stream is still draining; it must execute pdl_wait() before touching anything the predecessor wrote.
+// pdl_trigger() lets the successor's launch begin early.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 }  // namespace fs
 
 // ---- host side -------------------------------------------------------------------------------------------
@@ -161,6 +167,7 @@ void fs_compute_layout(int P, int W, int H, size_t Rcap, fs_workspace_layout* L)
 void fs_set_error(const char* fmt, ...);
 void fs_count_launch(int n);
 int fs_num_sms();
+uint32_t fs_tile_hint();
 int fs_tuning(const char* env_name, int default_value);  // integer tuning knob, read once from the environment
 
 // Optional per-stage timing (fs_profile_enable): CUDA events recorded on the launching stream around a stage.
@@ -184,6 +191,23 @@ struct FsStageTimer {  // RAII: records start in the ctor and stop in the dtor w
     int slot;
     cudaStream_t stream;
 };
+
+// Launch `kernel` so that it may overlap the tail of the previous kernel on `stream` (see fs::pdl_wait).
+template <typename... KArgs, typename... Args>
+inline cudaError_t fs_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = fs_tuning("FATESPLAT_PDL", 1) ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 #define FS_SORT_SMEM_CAP 2048  // instances a tile may hold to be sorted by the one-CTA-per-tile kernel
 // Per-tile counters live 128 bytes apart: L2 atomics to one line serialise, and only a few hundred tiles are hot.

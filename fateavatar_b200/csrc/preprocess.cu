@@ -81,6 +81,7 @@ preprocess_kernel(int P, int D, int M, const float* __restrict__ means3D, const 
     __shared__ __align__(16) float s_sh[kThreads * 3];
     __shared__ float s_view[16], s_proj[16], s_cam[3];
 
+    fs::pdl_trigger();  // the tile scan may begin launching; it waits for this grid before reading
     const int base = blockIdx.x * kThreads;
     const int idx = base + threadIdx.x;
     if (threadIdx.x < 16) {

@@ -53,6 +53,7 @@ class GaussianRasterizationSettings(NamedTuple):
 
 _ASYNC = os.environ.get("FATESPLAT_ASYNC", "0") == "1"
 _capacity_hint = {}   # (device index, W, H) -> instances seen recently
+_tile_hint = {}       # (device index, W, H) -> heaviest tile seen recently (fs_set_tile_hint)
 _pinned = {}          # device index -> (pinned uint8 tensor viewed as FsFrameInfo slots, next slot, events)
 _N_SLOTS = 64
 _INFO_BYTES = C.sizeof(FsFrameInfo)
@@ -92,6 +93,7 @@ def _drain_pending(ent, dev, block=False):
         if ev.query():
             info = _slot_info(ent, slot)
             _capacity_hint[key] = max(int(info.num_rendered), int(_capacity_hint.get(key, 0) * 0.9))
+            _tile_hint[key] = max(int(info.max_tile_instances), int(_tile_hint.get(key, 0) * 0.9))
             if info.overflow:
                 _capacity_hint[key] = int(info.num_rendered)
                 ent["pending"] = [p for p in ent["pending"] if p[0] != slot]
@@ -165,6 +167,7 @@ def forward_raw(raster_settings, means3D, sh, colors_precomp, opacities, scales,
             if _ASYNC:
                 _drain_pending(ent, di)
             capacity = _initial_capacity(P, W, H, di)
+            lib.fs_set_tile_hint(int(_tile_hint.get(key, 0) * 1.25))
             while True:
                 nbytes = lib.fs_workspace_bytes(P, W, H, capacity)
                 workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -190,6 +193,7 @@ def forward_raw(raster_settings, means3D, sh, colors_precomp, opacities, scales,
                 info = _slot_info(ent, slot)
                 num_rendered = int(info.num_rendered)
                 _capacity_hint[key] = max(num_rendered, int(_capacity_hint.get(key, 0) * 0.9))
+                _tile_hint[key] = max(int(info.max_tile_instances), int(_tile_hint.get(key, 0) * 0.9))
                 if not info.overflow:
                     break
                 capacity = (int(num_rendered * 1.25) + 1023) // 1024 * 1024  # re-run, exact results

@@ -69,6 +69,7 @@ typedef struct fs_workspace_layout {
     size_t ranges;        /* uint32 [Tn][2]  (start,end) into point_list; (0,0) if empty     */
     size_t big_tiles;     /* uint32 [Tn+1]   [0]=count, then ids of tiles too large for the smem sort */
     size_t work_order;    /* uint32 [Tn]     tile ids, heaviest first (work list of the blend kernels) */
+    size_t tile_meta;     /* uint32 [Tn][4]  (range start, range end, first segment id, 0): one 16-byte load per unit */
     size_t seg_base;      /* uint32 [Tn+1]   first depth-segment id of every tile (segments of 256 list positions) */
     size_t seg_info;      /* uint32 [Smax][2] (tile, segment index inside the tile), Smax = Rcap/256 + Tn + 1 */
     size_t ckpt;          /* float4 [Smax][256] per-pixel (T, accumulated colour) before each segment boundary:
@@ -118,6 +119,13 @@ int fs_backward(int P, int D, int M, const float* d_background, int width, int h
                 const float* d_dL_dpix, float* d_dL_dmean2D, float* d_dL_dopacity, float* d_dL_dcolors,
                 float* d_dL_dmean3D, float* d_dL_dcov3D, float* d_dL_dsh, float* d_dL_dscale, float* d_dL_drot,
                 void* stream);
+
+/*
+ * Optional performance hint for the next fs_forward calls on this thread: the heaviest tile's instance count
+ * observed in recent frames (fs_frame_info.max_tile_instances), 0 = unknown.  Only affects which sort kernels
+ * are launched, never the result.
+ */
+void fs_set_tile_hint(uint32_t max_tile_instances);
 
 /* present[i] = (view-space z of means3D[i] > 0.2); uint8 0/1 (rasterizer_impl.cu:54-66). */
 int fs_mark_visible(int P, const float* d_means3D, const float* d_viewmatrix, const float* d_projmatrix,

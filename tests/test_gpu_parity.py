@@ -305,3 +305,16 @@ def test_mark_visible_and_knn(cuda_device):
     if ref_loader.ref_knn() is not None:
         pts = torch.from_numpy(scenes.head_scene()["means3D"]).to(dev)
         assert torch.equal(knn.distCUDA2(pts), ref_loader.ref_knn().distCUDA2(pts))
+
+
+def test_wrong_tile_hint_only_costs_speed(cuda_device):
+    """fs_set_tile_hint may skip the oversized-tile sort launch; a hint that is far too small must not change
+    the result (tile_sort_kernel then sorts such tiles itself in global memory)."""
+    sc = scenes.head_scene(P=9000, W=64, H=64, scale_mult=10.0, seed=7)
+    o = oracle_forward(orc, sc)
+    assert (o["ranges"][:, 1] - o["ranges"][:, 0]).max() > 2048
+    key = (cuda_device.index, 64, 64)
+    for hint in (1, 0, 10 ** 6):
+        R._tile_hint[key] = hint
+        color, radii, st, taps, _ = run_new(sc, cuda_device)
+        check_forward_vs_oracle(color, radii, st, taps, o)
