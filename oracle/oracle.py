@@ -170,6 +170,15 @@ def knn_mean_dist2(points):
     return out
 
 
+def mask_fragile(o, dL_dpix):
+    """Upstream gradient with the oracle's threshold-fragile pixels zeroed.  A fragile pixel's list may gain or lose
+    one 1/255-contribution between glibc expf and CUDA expf (see compare_blend); feeding both sides a zero upstream
+    gradient there keeps that single discrete flip out of a gradient comparison that is otherwise tight."""
+    g = np.array(dL_dpix, np.float32, copy=True)
+    g[:, o["fragile"].astype(bool)] = 0.0
+    return g
+
+
 def compare_blend(o, color, final_T=None, n_contrib=None, tol=1e-5, fragile_tol=6e-3, max_fragile_frac=5e-3):
     """Compare a CUDA blend result with the oracle state `o`.  Pixels the oracle flags as fragile (a discrete
     decision within rounding distance of its threshold, see orc_blend_forward) may differ by one dropped/added

@@ -65,6 +65,7 @@ CASES = {
     "sh3": lambda: scenes.head_scene(P=3000, W=96, H=96, sh_degree=3, scale_mult=6.0, seed=6),
     "single_gaussian": lambda: scenes.config1_scene(P=1, W=64, H=64, seed=9),
     "p33": lambda: scenes.config1_scene(P=33, W=64, H=64, seed=10),
+    "smoke_scene_5k_128": lambda: scenes.head_scene(P=5000, W=128, H=128, scale_mult=5.0, seed=1),  # has fragile pixels
     "large_tile_lists": lambda: scenes.head_scene(P=9000, W=64, H=64, scale_mult=10.0, seed=7),   # > 4096 per tile
 }
 
@@ -75,9 +76,10 @@ def test_forward_backward_vs_oracle(name, cuda_device):
     if name == "single_gaussian":
         sc["means3D"][:] = 0.0
     cam = sc["camera"]
-    dpix = np.random.default_rng(3).standard_normal((3, cam["H"], cam["W"])).astype(np.float32)
-    color, radii, st, taps, grads = run_new(sc, cuda_device, dpix=dpix)
     o = oracle_forward(orc, sc)
+    # threshold-fragile pixels (glibc expf vs CUDA expf, see oracle.compare_blend) carry no upstream gradient
+    dpix = orc.mask_fragile(o, np.random.default_rng(3).standard_normal((3, cam["H"], cam["W"])).astype(np.float32))
+    color, radii, st, taps, grads = run_new(sc, cuda_device, dpix=dpix)
     check_forward_vs_oracle(color, radii, st, taps, o)
     og = orc.backward(o, dpix)
     for k in GRAD_NAMES:

@@ -174,6 +174,7 @@ def main():
     which = sys.argv[1:] or ["c1", "c2small", "c2", "c2sh3", "c5"]
     jobs = {
         "c1": lambda: run_scene("c1", scenes.config1_scene()),
+        "smoke": lambda: run_scene("smoke", scenes.head_scene(P=5000, W=128, H=128, scale_mult=5.0, seed=1)),
         "c2small": lambda: run_scene("c2small", scenes.head_scene(P=20000, W=300, H=200, scale_mult=3.0)),
         "c2": lambda: run_scene("c2", scenes.head_scene()),
         "c2big": lambda: run_scene("c2big", scenes.head_scene(scale_mult=4.0)),
