@@ -38,10 +38,11 @@ EXPORTS = [
     "fs_workspace_bytes", "fs_get_workspace_layout", "fs_forward", "fs_backward", "fs_mark_visible",
     "fs_knn_workspace_bytes", "fs_knn_mean_dist2", "fs_last_launch_count", "fs_last_error", "fs_version",
     "fs_profile_enable", "fs_profile_read", "fs_pose_forward", "fs_pose_backward", "fs_set_tile_hint",
+    "fs_flame_workspace_bytes", "fs_flame_forward", "fs_flame_backward",
 ]
 
 STAGES = ["preprocess", "tile_scan", "scatter", "tile_sort", "big_tile_sort", "blend_forward", "blend_backward",
-          "preprocess_backward", "knn", "pose_forward", "pose_backward"]
+          "preprocess_backward", "knn", "pose_forward", "pose_backward", "flame_forward", "flame_backward"]
 
 _lib = None
 
@@ -82,6 +83,12 @@ def load():
     lib.fs_pose_forward.argtypes = [i, i, i] + [vp] * 9 + [f, i] + [vp] * 4 + [vp]
     lib.fs_pose_backward.restype = i
     lib.fs_pose_backward.argtypes = [i, i, i] + [vp] * 9 + [f, i] + [vp] * 4 + [vp] * 5 + [vp]
+    lib.fs_flame_workspace_bytes.restype = sz
+    lib.fs_flame_workspace_bytes.argtypes = [i]
+    lib.fs_flame_forward.restype = i
+    lib.fs_flame_forward.argtypes = [i, i, i, i, C.POINTER(C.c_int)] + [vp] * 10 + [vp] * 5 + [vp, sz, vp]
+    lib.fs_flame_backward.restype = i
+    lib.fs_flame_backward.argtypes = [i, i, i, i, C.POINTER(C.c_int)] + [vp] * 4 + [vp, sz] + [vp] * 5 + [vp]
     lib.fs_set_tile_hint.restype = None
     lib.fs_set_tile_hint.argtypes = [C.c_uint32]
     lib.fs_profile_enable.restype = None

@@ -1,0 +1,537 @@
+// FLAME linear blend skinning with personalised blendshape deltas.
+//
+// Replaces, for batch size 1 (the only size FateAvatar uses, model/fateavatar.py:207 "bs = 1, essentially"):
+//   flame/FLAME.py:156-204  forward_with_delta_blendshape  (template + delta_vertex, shapedirs + delta, posedirs + delta)
+//   flame/FLAME.py:131-154  forward                        (the same pose without the deltas: verts_orig)
+//   flame/lbs.py:24-100     lbs: blendshape einsum (:63), joint regression (:67,207), Rodrigues with +1e-8
+//                           inside the norm (:253-270), pose correctives (:75-80), kinematic chain (:285-342),
+//                           skinning (:86-98)
+// which upstream is ~40 small torch kernels per call, two calls per frame, each re-reading the 24 MB shapedirs
+// tensor and materialising shapedirs + delta.  Here one frame is two kernels forward and two backward:
+//
+//   flame_blend_kernel          one warp per vertex streams the *active* coefficient range of shapedirs and
+//                               delta_shapedirs once (128-bit loads) and produces v_shaped for BOTH paths (with and
+//                               without deltas) plus per-CTA partial joint sums (fixed summation order);
+//   flame_skin_kernel           every CTA finishes the joints, Rodrigues and the kinematic chain (a few hundred
+//                               flops, cheaper than a third launch), then adds the pose correctives (posedirs +
+//                               delta read once, coalesced) and skins its 32 vertices for both paths;
+//   flame_skin_backward_kernel  dL/dv_posed = T^T g and per-CTA partials of dL/dA (the gradient that reaches the
+//                               joints through the kinematic chain);
+//   flame_blend_backward_kernel chain backward -> dL/dJ, dL/dv_shaped = dL/dv_posed + Jreg^T dL/dJ, then the three
+//                               parameter gradients: delta_vertex, delta_posedirs (rank-1: pose_feature (x) g) and
+//                               delta_shapedirs (rank-1: g (x) betas, 24 MB of streaming stores -- the only part of
+//                               the stage that is HBM-bound).
+// Everything is deterministic (no float atomics).  fp32 throughout; sums run in a different order than cuBLAS's
+// so parity with the reference is to tolerance (tests/test_flame.py), not bitwise.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxJ = FS_FLAME_MAX_JOINTS;
+constexpr int kBlendThreads = 512;                  // 16 warps, one vertex per warp per iteration
+constexpr int kSkinVerts = 32, kSkinThreads = 96;   // a skin CTA owns 32 vertices = 96 coordinates
+
+struct Parents {
+    int p[kMaxJ];
+};
+
+// Device-resident state of one forward call, kept in the workspace for the backward.  Index 0 = path with the
+// deltas, 1 = path without (verts_orig).
+struct FlameState {
+    float J[2][kMaxJ][3];    // regressed joints
+    float R[kMaxJ][9];       // local rotations (row-major)
+    float Rg[2][kMaxJ][9];   // chained rotations
+    float tg[2][kMaxJ][3];   // chained translations
+    float A[2][kMaxJ][12];   // rows 0..2 of the relative transforms (lbs.py:336-340)
+    float pf[(kMaxJ - 1) * 9];
+};
+
+struct FlameWs {  // byte offsets inside the workspace
+    size_t state, v_shaped, v_posed, g_posed, jpart, dapart, total;
+    int nblk_blend, nblk_skin;
+};
+
+FlameWs flame_layout(int V) {
+    FlameWs w;
+    auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+    w.nblk_blend = fs_num_sms();
+    w.nblk_skin = (V + kSkinVerts - 1) / kSkinVerts;
+    size_t o = 0;
+    w.state = o;
+    o = al(o + sizeof(FlameState));
+    w.v_shaped = o;
+    o = al(o + (size_t)2 * V * 3 * sizeof(float));
+    w.v_posed = o;
+    o = al(o + (size_t)V * 3 * sizeof(float));
+    w.g_posed = o;
+    o = al(o + (size_t)V * 3 * sizeof(float));
+    w.jpart = o;
+    o = al(o + (size_t)w.nblk_blend * 2 * kMaxJ * 3 * sizeof(float));
+    w.dapart = o;
+    o = al(o + (size_t)w.nblk_skin * kMaxJ * 12 * sizeof(float));
+    w.total = o;
+    return w;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- forward 1: blendshapes ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlendThreads)
+flame_blend_kernel(int V, int L, int l0, int J, const float* __restrict__ betas, const float* __restrict__ v_template,
+                   const float* __restrict__ delta_vertex, const float* __restrict__ shapedirs,
+                   const float* __restrict__ delta_shapedirs, const float* __restrict__ J_regressor,
+                   float* __restrict__ v_shaped /*[2][3V]*/, float* __restrict__ jpart /*[2*3J][grid]*/) {
+    __shared__ float s_j[kBlendThreads / 32][2 * kMaxJ * 3];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nw = gridDim.x * (kBlendThreads / 32);
+    const int n = L - l0;
+    const bool vec = ((L | l0) & 3) == 0;  // rows start 16-byte aligned and hold whole float4s
+    const int nslot = 2 * J * 3;
+    float jp0 = 0.f, jp1 = 0.f;  // joint partial sums of slots lane, lane + 32
+
+    for (int v = blockIdx.x * (kBlendThreads / 32) + wid; v < V; v += nw) {
+        float ao[3] = {0.f, 0.f, 0.f}, ad[3] = {0.f, 0.f, 0.f};  // sum beta * S, sum beta * (S + dS)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const size_t row = ((size_t)v * 3 + k) * L + l0;
+            if (vec) {
+                const float4* s4 = reinterpret_cast<const float4*>(shapedirs + row);
+                const float4* d4 = delta_shapedirs ? reinterpret_cast<const float4*>(delta_shapedirs + row) : nullptr;
+                const float4* b4 = reinterpret_cast<const float4*>(betas + l0);
+                for (int c = lane; c < (n >> 2); c += 32) {
+                    const float4 s = __ldg(s4 + c), b = __ldg(b4 + c);
+                    ao[k] += b.x * s.x + b.y * s.y + b.z * s.z + b.w * s.w;
+                    if (d4) {
+                        const float4 d = __ldg(d4 + c);
+                        ad[k] += b.x * (s.x + d.x) + b.y * (s.y + d.y) + b.z * (s.z + d.z) + b.w * (s.w + d.w);
+                    }
+                }
+            } else {
+                for (int c = lane; c < n; c += 32) {
+                    const float s = __ldg(shapedirs + row + c), b = __ldg(betas + l0 + c);
+                    ao[k] += b * s;
+                    if (delta_shapedirs) ad[k] += b * (s + __ldg(delta_shapedirs + row + c));
+                }
+            }
+        }
+        float vs[2][3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float so = warp_sum(ao[k]);
+            const float sd = delta_shapedirs ? warp_sum(ad[k]) : so;
+            const float t = __ldg(v_template + 3 * v + k);
+            vs[0][k] = (delta_vertex ? t + __ldg(delta_vertex + 3 * v + k) : t) + sd;
+            vs[1][k] = t + so;
+        }
+        if (lane < 6) {
+            const int path = lane / 3, k = lane % 3;
+            const float val = k == 0 ? vs[path][0] : k == 1 ? vs[path][1] : vs[path][2];
+            v_shaped[(size_t)path * 3 * V + 3 * v + k] = val;
+        }
+        // joint regression (lbs.py:207): slot = path * 3J + j * 3 + k
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int slot = lane + 32 * h;
+            if (slot < nslot) {
+                const int path = slot / (3 * J), r = slot % (3 * J), j = r / 3, k = r % 3;
+                const float a = path ? (k == 0 ? vs[1][0] : k == 1 ? vs[1][1] : vs[1][2])
+                                     : (k == 0 ? vs[0][0] : k == 1 ? vs[0][1] : vs[0][2]);
+                const float w = __ldg(J_regressor + (size_t)j * V + v);
+                if (h == 0) jp0 += w * a; else jp1 += w * a;
+            }
+        }
+    }
+    if (lane < nslot) s_j[wid][lane] = jp0;
+    if (lane + 32 < nslot) s_j[wid][lane + 32] = jp1;
+    __syncthreads();
+    if (threadIdx.x < nslot) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kBlendThreads / 32; ++w) s += s_j[w][threadIdx.x];
+        jpart[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = s;  // [slot][CTA]: the consumer reads along CTAs
+    }
+    fs::pdl_trigger();
+}
+
+// Rodrigues exactly as lbs.py:253-270: angle = ||r + 1e-8||, K from r / angle, R = I + sin K + (1 - cos) K K.
+__device__ void rodrigues(const float* r, float* R) {
+    const float ax = r[0] + 1e-8f, ay = r[1] + 1e-8f, az = r[2] + 1e-8f;
+    const float angle = sqrtf(ax * ax + ay * ay + az * az);
+    const float rx = r[0] / angle, ry = r[1] / angle, rz = r[2] / angle;
+    const float s = sinf(angle), c1 = 1.0f - cosf(angle);
+    const float K[9] = {0.f, -rz, ry, rz, 0.f, -rx, -ry, rx, 0.f};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const float kk = K[a * 3] * K[b] + K[a * 3 + 1] * K[3 + b] + K[a * 3 + 2] * K[6 + b];
+            R[a * 3 + b] = (a == b ? 1.0f : 0.0f) + s * K[a * 3 + b] + c1 * kk;
+        }
+}
+
+// ---- forward 2: joints, chain, pose correctives, skinning ------------------------------------------------
+__global__ void __launch_bounds__(kSkinThreads)
+flame_skin_kernel(int V, int J, Parents parents, int nblk_blend, const float* __restrict__ pose,
+                  const float* __restrict__ posedirs, const float* __restrict__ delta_posedirs,
+                  const float* __restrict__ lbs_weights, const float* __restrict__ v_shaped,
+                  const float* __restrict__ jpart, FlameState* __restrict__ state, float* __restrict__ v_posed_out,
+                  float* __restrict__ verts, float* __restrict__ verts_orig, float* __restrict__ pose_feature_out,
+                  float* __restrict__ transforms, float* __restrict__ transforms_orig) {
+    __shared__ FlameState S;
+    __shared__ float s_vp[2][kSkinThreads];
+    const int t = threadIdx.x;
+    const int NP = (J - 1) * 9;
+    // rotations do not depend on the previous kernel: compute them before waiting for it
+    if (t >= 64 && t < 64 + J) {
+        const int j = t - 64;
+        const float r[3] = {__ldg(pose + 3 * j), __ldg(pose + 3 * j + 1), __ldg(pose + 3 * j + 2)};
+        rodrigues(r, S.R[j]);
+        if (j > 0)
+#pragma unroll
+            for (int e = 0; e < 9; ++e) S.pf[(j - 1) * 9 + e] = S.R[j][e] - ((e % 4) == 0 ? 1.0f : 0.0f);
+    }
+    fs::pdl_wait();
+    {   // finish the joint regression: one warp per slot, lanes along the producer CTAs, fixed order
+        const int lane = t & 31, wid = t >> 5;
+        for (int slot = wid; slot < 2 * J * 3; slot += kSkinThreads / 32) {
+            float s = 0.f;
+            for (int b = lane; b < nblk_blend; b += 32) s += jpart[(size_t)slot * nblk_blend + b];
+            s = warp_sum(s);
+            if (lane == 0) (&S.J[0][0][0])[(slot / (3 * J)) * kMaxJ * 3 + (slot % (3 * J))] = s;
+        }
+    }
+    __syncthreads();
+    if (t < 64) {  // kinematic chain (lbs.py:285-342): warp p_ = path, lanes 0..8 = rotation entries, 9..11 = translation
+        const int p_ = t >> 5, lane = t & 31;
+        for (int j = 0; j < J; ++j) {  // parents[j] < j
+            const int pa = parents.p[j];
+            if (lane < 12) {
+                float rel[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) rel[k] = S.J[p_][j][k] - (j > 0 ? S.J[p_][pa][k] : 0.0f);
+                if (lane < 9) {
+                    const int a = lane / 3, b = lane % 3;
+                    const float* G = S.Rg[p_][pa];
+                    S.Rg[p_][j][lane] = j == 0 ? S.R[0][lane]
+                                               : G[a * 3] * S.R[j][b] + G[a * 3 + 1] * S.R[j][3 + b] + G[a * 3 + 2] * S.R[j][6 + b];
+                } else {
+                    const int a = lane - 9;
+                    const float* G = S.Rg[p_][pa];
+                    S.tg[p_][j][a] = j == 0 ? rel[a]
+                                            : G[a * 3] * rel[0] + G[a * 3 + 1] * rel[1] + G[a * 3 + 2] * rel[2] + S.tg[p_][pa][a];
+                }
+            }
+            __syncwarp();
+        }
+        for (int i = lane; i < J * 12; i += 32) {  // A = [Rg | tg - Rg J]
+            const int j = i / 12, a = (i % 12) / 4, c = i % 4;
+            const float* G = S.Rg[p_][j];
+            S.A[p_][j][a * 4 + c] = c < 3 ? G[a * 3 + c]
+                                          : S.tg[p_][j][a] - (G[a * 3] * S.J[p_][j][0] + G[a * 3 + 1] * S.J[p_][j][1] + G[a * 3 + 2] * S.J[p_][j][2]);
+        }
+    }
+    __syncthreads();
+    if (blockIdx.x == 0) {  // publish the small results once
+        float* dst = reinterpret_cast<float*>(state);
+        const float* src = reinterpret_cast<const float*>(&S);
+        for (int i = t; i < (int)(sizeof(FlameState) / sizeof(float)); i += kSkinThreads) dst[i] = src[i];
+        if (pose_feature_out)
+            for (int i = t; i < NP; i += kSkinThreads) pose_feature_out[i] = S.pf[i];
+        for (int i = t; i < J * 16; i += kSkinThreads) {
+            const int j = i >> 4, e = i & 15;
+            if (transforms) transforms[i] = e < 12 ? S.A[0][j][e] : (e == 15 ? 1.0f : 0.0f);
+            if (transforms_orig) transforms_orig[i] = e < 12 ? S.A[1][j][e] : (e == 15 ? 1.0f : 0.0f);
+        }
+    }
+
+    const int e = blockIdx.x * kSkinThreads + t;  // coordinate index 3 v + k
+    const int n3 = 3 * V;
+    float vpd = 0.f, vpo = 0.f;
+    if (e < n3) {
+        float po = 0.f, pd = 0.f;  // pose_feature @ posedirs, pose_feature @ (posedirs + delta)
+        for (int i = 0; i < NP; ++i) {
+            const float p = __ldg(posedirs + (size_t)i * n3 + e);
+            po += S.pf[i] * p;
+            if (delta_posedirs) pd += S.pf[i] * (p + __ldg(delta_posedirs + (size_t)i * n3 + e));
+        }
+        if (!delta_posedirs) pd = po;
+        vpd = pd + v_shaped[e];
+        vpo = po + v_shaped[(size_t)n3 + e];
+        v_posed_out[e] = vpd;
+    }
+    s_vp[0][t] = vpd;
+    s_vp[1][t] = vpo;
+    __syncthreads();
+    if (e < n3) {
+        const int vl = t / 3, k = t % 3, v = e / 3;
+        float Td[4] = {0.f, 0.f, 0.f, 0.f}, To[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < J; ++j) {
+            const float w = __ldg(lbs_weights + (size_t)v * J + j);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                Td[c] += w * S.A[0][j][k * 4 + c];
+                To[c] += w * S.A[1][j][k * 4 + c];
+            }
+        }
+        verts[e] = Td[0] * s_vp[0][3 * vl] + Td[1] * s_vp[0][3 * vl + 1] + Td[2] * s_vp[0][3 * vl + 2] + Td[3];
+        if (verts_orig)
+            verts_orig[e] = To[0] * s_vp[1][3 * vl] + To[1] * s_vp[1][3 * vl + 1] + To[2] * s_vp[1][3 * vl + 2] + To[3];
+    }
+}
+
+// ---- backward 1: through the skinning ----------------------------------------------------------------------
+__global__ void __launch_bounds__(kSkinThreads)
+flame_skin_backward_kernel(int V, int J, const float* __restrict__ lbs_weights, const FlameState* __restrict__ state,
+                           const float* __restrict__ v_posed, const float* __restrict__ dL_dverts,
+                           float* __restrict__ g_posed, float* __restrict__ dapart /*[12J][grid]*/) {
+    __shared__ float s_A[kMaxJ][12];
+    __shared__ float s_g[kSkinThreads], s_vp[kSkinThreads], s_w[kSkinVerts][kMaxJ];
+    const int t = threadIdx.x;
+    const int v0 = blockIdx.x * kSkinVerts;
+    const int e = blockIdx.x * kSkinThreads + t, n3 = 3 * V;
+    for (int i = t; i < J * 12; i += kSkinThreads) s_A[i / 12][i % 12] = state->A[0][i / 12][i % 12];
+    s_g[t] = e < n3 ? dL_dverts[e] : 0.0f;
+    s_vp[t] = e < n3 ? v_posed[e] : 0.0f;
+    for (int i = t; i < kSkinVerts * J; i += kSkinThreads) {
+        const int vl = i / J, j = i % J;
+        s_w[vl][j] = (v0 + vl) < V ? __ldg(lbs_weights + (size_t)(v0 + vl) * J + j) : 0.0f;
+    }
+    __syncthreads();
+    if (e < n3) {  // dL/dv_posed[c] = sum_k T[k][c] g[k]
+        const int vl = t / 3, c = t % 3;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float T = 0.f;
+            for (int j = 0; j < J; ++j) T += s_w[vl][j] * s_A[j][k * 4 + c];
+            acc += T * s_g[3 * vl + k];
+        }
+        g_posed[e] = acc;
+    }
+    if (t < J * 12) {  // dL/dA[j][k][c] = sum_v W[v][j] g[v][k] (c < 3 ? v_posed[v][c] : 1), this CTA's vertices
+        const int j = t / 12, k = (t % 12) / 4, c = t % 4;
+        float acc = 0.f;
+        for (int vl = 0; vl < kSkinVerts; ++vl)
+            acc += s_w[vl][j] * s_g[3 * vl + k] * (c < 3 ? s_vp[3 * vl + c] : 1.0f);
+        dapart[(size_t)t * gridDim.x + blockIdx.x] = acc;  // [slot][CTA]
+    }
+    fs::pdl_trigger();
+}
+
+// ---- backward 2: chain backward + parameter gradients -------------------------------------------------------
+__global__ void __launch_bounds__(kBlendThreads)
+flame_blend_backward_kernel(int V, int L, int l0, int J, Parents parents, int nblk_skin,
+                            const float* __restrict__ betas, const float* __restrict__ J_regressor,
+                            const FlameState* __restrict__ state, const float* __restrict__ g_posed,
+                            const float* __restrict__ dapart, float* __restrict__ d_delta_vertex,
+                            float* __restrict__ d_delta_shapedirs, float* __restrict__ d_delta_posedirs,
+                            float* __restrict__ d_v_shaped) {
+    __shared__ float s_dA[kMaxJ][12];
+    __shared__ float s_dJ[kMaxJ][3], s_dRg[kMaxJ][9], s_dtg[kMaxJ][3];
+    __shared__ float s_pf[(kMaxJ - 1) * 9];
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int NP = (J - 1) * 9, n3 = 3 * V;
+    fs::pdl_wait();
+    for (int slot = wid; slot < J * 12; slot += kBlendThreads / 32) {  // lanes along the producer CTAs, fixed order
+        float s = 0.f;
+        for (int b = lane; b < nblk_skin; b += 32) s += dapart[(size_t)slot * nblk_skin + b];
+        s = warp_sum(s);
+        if (lane == 0) s_dA[slot / 12][slot % 12] = s;
+    }
+    if (t >= 128 && t < 128 + NP) s_pf[t - 128] = state->pf[t - 128];
+    __syncthreads();
+    if (wid == 0) {
+        // A[j] = [Rg_j | tg_j - Rg_j J_j];  Rg_j = Rg_p R_j;  tg_j = Rg_p (J_j - J_p) + tg_p  (j > 0);  tg_0 = J_0
+        // lanes 0..8 own the entries of dRg, 9..11 those of drel / dJ, 12..14 those of dtg
+        for (int i = lane; i < J * 12; i += 32) {
+            const int j = i / 12, r = i % 12;
+            if (r < 9) s_dRg[j][r] = s_dA[j][(r / 3) * 4 + r % 3] - s_dA[j][(r / 3) * 4 + 3] * state->J[0][j][r % 3];
+            else s_dtg[j][r - 9] = s_dA[j][(r - 9) * 4 + 3];
+        }
+        __syncwarp();
+        for (int i = lane; i < J * 3; i += 32) {
+            const int j = i / 3, b = i % 3;
+            const float* G = state->Rg[0][j];
+            s_dJ[j][b] = -(G[b] * s_dtg[j][0] + G[3 + b] * s_dtg[j][1] + G[6 + b] * s_dtg[j][2]);
+        }
+        __syncwarp();
+        for (int j = J - 1; j >= 1; --j) {
+            const int pa = parents.p[j];
+            if (lane < 9) {  // dRg_p += dRg_j R_j^T + dtg_j (x) rel
+                const int a = lane / 3, b = lane % 3;
+                const float* Rj = state->R[j];
+                const float rel = state->J[0][j][b] - state->J[0][pa][b];
+                s_dRg[pa][lane] += s_dRg[j][a * 3] * Rj[b * 3] + s_dRg[j][a * 3 + 1] * Rj[b * 3 + 1] +
+                                   s_dRg[j][a * 3 + 2] * Rj[b * 3 + 2] + s_dtg[j][a] * rel;
+            } else if (lane < 12) {  // drel = Rg_p^T dtg_j
+                const int b = lane - 9;
+                const float* Gp = state->Rg[0][pa];
+                const float drel = Gp[b] * s_dtg[j][0] + Gp[3 + b] * s_dtg[j][1] + Gp[6 + b] * s_dtg[j][2];
+                s_dJ[j][b] += drel;
+                s_dJ[pa][b] -= drel;
+            }
+            __syncwarp();
+            if (lane >= 12 && lane < 15) s_dtg[pa][lane - 12] += s_dtg[j][lane - 12];
+            __syncwarp();
+        }
+        if (lane < 3) s_dJ[0][lane] += s_dtg[0][lane];
+    }
+    __syncthreads();
+
+    // rank-1 gradient of delta_posedirs: pose_feature (x) dL/dv_posed, coalesced along the coordinate axis
+    if (d_delta_posedirs) {
+        const int nthreads = gridDim.x * kBlendThreads;
+        for (int e = blockIdx.x * kBlendThreads + t; e < n3; e += nthreads) {
+            const float g = g_posed[e];
+            for (int i = 0; i < NP; ++i) __stcs(d_delta_posedirs + (size_t)i * n3 + e, s_pf[i] * g);
+        }
+    }
+    // per coordinate row: dL/dv_shaped, delta_vertex, and the rank-1 gradient of delta_shapedirs
+    const int nw = gridDim.x * (kBlendThreads / 32);
+    const bool vec = (L & 3) == 0 && (l0 & 3) == 0;
+    for (int r = blockIdx.x * (kBlendThreads / 32) + wid; r < n3; r += nw) {
+        const int v = r / 3, k = r % 3;
+        float gs = g_posed[r];
+        for (int j = 0; j < J; ++j) gs += __ldg(J_regressor + (size_t)j * V + v) * s_dJ[j][k];
+        if (lane == 0) {
+            if (d_delta_vertex) d_delta_vertex[r] = gs;
+            if (d_v_shaped) d_v_shaped[r] = gs;
+        }
+        if (d_delta_shapedirs) {
+            float* row = d_delta_shapedirs + (size_t)r * L;
+            if (vec) {
+                const float4* b4 = reinterpret_cast<const float4*>(betas);
+                for (int c = lane; c < (L >> 2); c += 32) {
+                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (4 * c >= l0) {
+                        const float4 b = __ldg(b4 + c);
+                        o = make_float4(b.x * gs, b.y * gs, b.z * gs, b.w * gs);
+                    }
+                    __stcs(reinterpret_cast<float4*>(row) + c, o);
+                }
+            } else {
+                for (int c = lane; c < L; c += 32) __stcs(row + c, c >= l0 ? __ldg(betas + c) * gs : 0.0f);
+            }
+        }
+    }
+}
+
+bool parents_ok(int J, const int* parents_host, Parents& P) {
+    if (J < 1 || J > kMaxJ || !parents_host) return false;
+    for (int j = 0; j < kMaxJ; ++j) P.p[j] = 0;
+    for (int j = 0; j < J; ++j) {
+        P.p[j] = parents_host[j];
+        if (j > 0 && (parents_host[j] < 0 || parents_host[j] >= j)) return false;
+    }
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t fs_flame_workspace_bytes(int V) { return V > 0 ? flame_layout(V).total : 0; }
+
+int fs_flame_forward(int V, int L, int l0, int J, const int* parents_host, const float* d_betas, const float* d_pose,
+                     const float* d_v_template, const float* d_delta_vertex, const float* d_shapedirs,
+                     const float* d_delta_shapedirs, const float* d_posedirs, const float* d_delta_posedirs,
+                     const float* d_J_regressor, const float* d_lbs_weights, float* d_verts, float* d_verts_orig,
+                     float* d_pose_feature, float* d_transforms, float* d_transforms_orig, void* d_workspace,
+                     size_t workspace_bytes, void* stream) {
+    Parents P;
+    if (V <= 0 || L <= 0 || l0 < 0 || l0 > L || !parents_ok(J, parents_host, P)) {
+        fs_set_error("fs_flame_forward: invalid size or kinematic tree (V=%d L=%d l0=%d J=%d; need parents[j] < j, J <= %d)",
+                     V, L, l0, J, kMaxJ);
+        return FS_ERR_INVALID_ARGUMENT;
+    }
+    if (!d_betas || !d_pose || !d_v_template || !d_shapedirs || !d_posedirs || !d_J_regressor || !d_lbs_weights ||
+        !d_verts || !d_workspace) {
+        fs_set_error("fs_flame_forward: required pointer is NULL");
+        return FS_ERR_INVALID_ARGUMENT;
+    }
+    const FlameWs w = flame_layout(V);
+    if (workspace_bytes < w.total) {
+        fs_set_error("fs_flame_forward: workspace too small (%zu < %zu bytes)", workspace_bytes, w.total);
+        return FS_ERR_WORKSPACE_TOO_SMALL;
+    }
+    if ((reinterpret_cast<uintptr_t>(d_workspace) & 255) != 0) {
+        fs_set_error("fs_flame_forward: workspace must be 256-byte aligned");
+        return FS_ERR_INVALID_ARGUMENT;
+    }
+    // the 128-bit path needs 16-byte aligned tensor bases (torch allocations are); otherwise use scalars
+    const bool aligned = ((reinterpret_cast<uintptr_t>(d_shapedirs) | reinterpret_cast<uintptr_t>(d_delta_shapedirs) |
+                           reinterpret_cast<uintptr_t>(d_betas)) & 15) == 0;
+    if (!aligned && ((L | l0) & 3) == 0) {
+        fs_set_error("fs_flame_forward: shapedirs / delta_shapedirs / betas must be 16-byte aligned");
+        return FS_ERR_INVALID_ARGUMENT;
+    }
+    char* ws = static_cast<char*>(d_workspace);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FsStageTimer timer(FS_STAGE_FLAME_FWD, st);
+    flame_blend_kernel<<<w.nblk_blend, kBlendThreads, 0, st>>>(
+        V, L, l0, J, d_betas, d_v_template, d_delta_vertex, d_shapedirs, d_delta_shapedirs, d_J_regressor,
+        reinterpret_cast<float*>(ws + w.v_shaped), reinterpret_cast<float*>(ws + w.jpart));
+    fs_launch_pdl(flame_skin_kernel, dim3(w.nblk_skin), dim3(kSkinThreads), 0, st, V, J, P, w.nblk_blend, d_pose,
+                  d_posedirs, d_delta_posedirs, d_lbs_weights, reinterpret_cast<const float*>(ws + w.v_shaped),
+                  reinterpret_cast<const float*>(ws + w.jpart), reinterpret_cast<FlameState*>(ws + w.state),
+                  reinterpret_cast<float*>(ws + w.v_posed), d_verts, d_verts_orig, d_pose_feature, d_transforms,
+                  d_transforms_orig);
+    fs_count_launch(2);
+    if (cudaGetLastError() != cudaSuccess) {
+        fs_set_error("fs_flame_forward: launch failed");
+        return FS_ERR_CUDA;
+    }
+    return FS_OK;
+}
+
+int fs_flame_backward(int V, int L, int l0, int J, const int* parents_host, const float* d_betas,
+                      const float* d_J_regressor, const float* d_lbs_weights, const float* d_dL_dverts,
+                      void* d_workspace, size_t workspace_bytes, float* d_dL_ddelta_vertex,
+                      float* d_dL_ddelta_shapedirs, float* d_dL_ddelta_posedirs, float* d_dL_dv_shaped,
+                      float* d_dL_dv_posed, void* stream) {
+    Parents P;
+    if (V <= 0 || L <= 0 || l0 < 0 || l0 > L || !parents_ok(J, parents_host, P)) {
+        fs_set_error("fs_flame_backward: invalid size or kinematic tree");
+        return FS_ERR_INVALID_ARGUMENT;
+    }
+    if (!d_betas || !d_J_regressor || !d_lbs_weights || !d_dL_dverts || !d_workspace) {
+        fs_set_error("fs_flame_backward: required pointer is NULL");
+        return FS_ERR_INVALID_ARGUMENT;
+    }
+    const FlameWs w = flame_layout(V);
+    if (workspace_bytes < w.total) {
+        fs_set_error("fs_flame_backward: workspace too small (%zu < %zu bytes)", workspace_bytes, w.total);
+        return FS_ERR_WORKSPACE_TOO_SMALL;
+    }
+    if (((L | l0) & 3) == 0 &&
+        ((reinterpret_cast<uintptr_t>(d_betas) | reinterpret_cast<uintptr_t>(d_dL_ddelta_shapedirs)) & 15) != 0) {
+        fs_set_error("fs_flame_backward: betas / dL_ddelta_shapedirs must be 16-byte aligned");
+        return FS_ERR_INVALID_ARGUMENT;
+    }
+    char* ws = static_cast<char*>(d_workspace);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FsStageTimer timer(FS_STAGE_FLAME_BWD, st);
+    float* g_posed = d_dL_dv_posed ? d_dL_dv_posed : reinterpret_cast<float*>(ws + w.g_posed);
+    flame_skin_backward_kernel<<<w.nblk_skin, kSkinThreads, 0, st>>>(
+        V, J, d_lbs_weights, reinterpret_cast<const FlameState*>(ws + w.state),
+        reinterpret_cast<const float*>(ws + w.v_posed), d_dL_dverts, g_posed, reinterpret_cast<float*>(ws + w.dapart));
+    // enough CTAs to stream the 4 L V 3-byte delta_shapedirs gradient at full rate, few enough that the
+    // redundant prologue (partials reduce + chain backward) stays negligible
+    const int grid = d_dL_ddelta_shapedirs ? 2 * fs_num_sms() : fs_num_sms() / 2 + 1;
+    fs_launch_pdl(flame_blend_backward_kernel, dim3(grid), dim3(kBlendThreads), 0, st, V, L, l0, J, P, w.nblk_skin,
+                  d_betas, d_J_regressor, reinterpret_cast<const FlameState*>(ws + w.state),
+                  (const float*)g_posed, reinterpret_cast<const float*>(ws + w.dapart), d_dL_ddelta_vertex,
+                  d_dL_ddelta_shapedirs, d_dL_ddelta_posedirs, d_dL_dv_shaped);
+    fs_count_launch(2);
+    if (cudaGetLastError() != cudaSuccess) {
+        fs_set_error("fs_flame_backward: launch failed");
+        return FS_ERR_CUDA;
+    }
+    return FS_OK;
+}
+
+}  // extern "C"

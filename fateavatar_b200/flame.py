@@ -1,0 +1,170 @@
+"""FLAME skinning stage on the fused sm_100a kernels, behind the reference's own interface.
+
+Mirrors flame/FLAME.py:131-204 (`FLAME.forward`, `FLAME.forward_with_delta_blendshape`) and flame/lbs.py:24-100:
+
+    verts, pose_feature, transformations = flame.forward_with_delta_blendshape(expression, full_pose,
+                                                delta_shapedirs, delta_posedirs, delta_vertex)
+    verts_orig, _, _                     = flame.forward(expression, full_pose)
+
+FateAvatar calls both, back to back, every frame (model/fateavatar.py:211-222).  `fs_flame_forward` produces both
+results in one pass over the blendshape tensors; `attach(flame_module)` rebinds the two methods of an existing
+reference FLAME module so the caller runs unchanged (the second call is served from the first one's by-product).
+Gradients flow to delta_shapedirs / delta_posedirs / delta_vertex (the parameters FateAvatar trains); expression
+and pose are dataset inputs upstream -- asking for their gradient raises instead of silently returning None.
+CUDA only; no CPU path.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import FateSplatError
+
+
+def _parents_c(parents):
+    p = [int(x) for x in (parents.tolist() if torch.is_tensor(parents) else list(parents))]
+    return (C.c_int * len(p))(*p), len(p)
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def flame_forward_raw(betas, pose, v_template, shapedirs, posedirs, J_regressor, parents, lbs_weights,
+                      delta_vertex=None, delta_shapedirs=None, delta_posedirs=None, l0=0, want_orig=True,
+                      workspace=None):
+    """One fs_flame_forward call on contiguous fp32 CUDA tensors (no autograd).
+    Returns dict(verts, verts_orig, pose_feature, transforms, transforms_orig, workspace)."""
+    lib = _lib.load()
+    dev = v_template.device
+    V, L = v_template.shape[0], shapedirs.shape[-1]
+    pc, J = _parents_c(parents)
+    nbytes = lib.fs_flame_workspace_bytes(V)
+    ws = workspace if workspace is not None and workspace.numel() >= nbytes else torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    verts = torch.empty((V, 3), device=dev)
+    verts_orig = torch.empty((V, 3), device=dev) if want_orig else None
+    pf = torch.empty(((J - 1) * 9,), device=dev)
+    A = torch.empty((J, 4, 4), device=dev)
+    A_orig = torch.empty((J, 4, 4), device=dev) if want_orig else None
+    with torch.cuda.device(dev):
+        rc = lib.fs_flame_forward(V, L, int(l0), J, pc, betas.data_ptr(), pose.data_ptr(), v_template.data_ptr(),
+                                  _ptr(delta_vertex), shapedirs.data_ptr(), _ptr(delta_shapedirs), posedirs.data_ptr(),
+                                  _ptr(delta_posedirs), J_regressor.data_ptr(), lbs_weights.data_ptr(), verts.data_ptr(),
+                                  _ptr(verts_orig), pf.data_ptr(), A.data_ptr(), _ptr(A_orig), ws.data_ptr(), ws.numel(),
+                                  torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "fs_flame_forward")
+    return dict(verts=verts, verts_orig=verts_orig, pose_feature=pf, transforms=A, transforms_orig=A_orig, workspace=ws)
+
+
+def flame_backward_raw(betas, J_regressor, parents, lbs_weights, workspace, dL_dverts, shapes, l0=0,
+                       want=(True, True, True), out=None, factors=False):
+    """One fs_flame_backward call.  `shapes` = (V, L); `want` selects (delta_vertex, delta_shapedirs,
+    delta_posedirs) gradients; `out` may supply preallocated tensors for them.  With factors=True also returns
+    (dL_dv_shaped, dL_dv_posed), the [V,3] factors of the two rank-1 gradients."""
+    lib = _lib.load()
+    dev = dL_dverts.device
+    V, L = shapes
+    pc, J = _parents_c(parents)
+    o = list(out) if out is not None else [None, None, None]
+    if want[0] and o[0] is None:
+        o[0] = torch.empty((V, 3), device=dev)
+    if want[1] and o[1] is None:
+        o[1] = torch.empty((V, 3, L), device=dev)
+    if want[2] and o[2] is None:
+        o[2] = torch.empty(((J - 1) * 9, V * 3), device=dev)
+    gs = torch.empty((V, 3), device=dev) if factors else None
+    gp = torch.empty((V, 3), device=dev) if factors else None
+    with torch.cuda.device(dev):
+        rc = lib.fs_flame_backward(V, L, int(l0), J, pc, betas.data_ptr(), J_regressor.data_ptr(), lbs_weights.data_ptr(),
+                                   dL_dverts.data_ptr(), workspace.data_ptr(), workspace.numel(),
+                                   _ptr(o[0]) if want[0] else None, _ptr(o[1]) if want[1] else None,
+                                   _ptr(o[2]) if want[2] else None, _ptr(gs), _ptr(gp),
+                                   torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "fs_flame_backward")
+    return (o[0], o[1], o[2]) + ((gs, gp) if factors else ())
+
+
+class _FlameLBS(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, betas, pose, delta_vertex, delta_shapedirs, delta_posedirs, model, l0, want_orig):
+        if not model["v_template"].is_cuda:
+            raise FateSplatError("flame_lbs needs CUDA tensors: fateavatar_b200 has no CPU path")
+        if betas.requires_grad or pose.requires_grad:
+            raise FateSplatError("fs_flame_backward produces no gradient for expression / pose coefficients "
+                                 "(FateAvatar does not optimise them); detach them before the call")
+        f = lambda t: None if t is None else t.detach().contiguous().float()
+        b, p = f(betas).reshape(-1), f(pose).reshape(-1)
+        dv, ds, dp = f(delta_vertex), f(delta_shapedirs), f(delta_posedirs)
+        r = flame_forward_raw(b, p, model["v_template"], model["shapedirs"], model["posedirs"], model["J_regressor"],
+                              model["parents"], model["lbs_weights"], dv, ds, dp, l0=l0, want_orig=want_orig)
+        ctx.model, ctx.l0, ctx.ws, ctx.betas = model, l0, r["workspace"], b
+        ctx.have = (delta_vertex is not None, delta_shapedirs is not None, delta_posedirs is not None)
+        outs = (r["verts"], r["pose_feature"], r["transforms"])
+        if want_orig:
+            outs += (r["verts_orig"], r["transforms_orig"])
+        ctx.mark_non_differentiable(*outs[1:])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_verts, *_unused):
+        m = ctx.model
+        V, L = m["v_template"].shape[0], m["shapedirs"].shape[-1]
+        want = tuple(h and ctx.needs_input_grad[2 + i] for i, h in enumerate(ctx.have))
+        if g_verts is None or not any(want):
+            return (None,) * 8
+        gdv, gds, gdp = flame_backward_raw(ctx.betas, m["J_regressor"], m["parents"], m["lbs_weights"], ctx.ws,
+                                           g_verts.contiguous().float().reshape(V, 3), (V, L), l0=ctx.l0, want=want)
+        return None, None, gdv, gds, gdp, None, None, None
+
+
+def model_tensors(flame_module):
+    """The buffers flame/FLAME.py:72-107 registers, as contiguous fp32 CUDA tensors (parents stays a host list)."""
+    g = lambda n: getattr(flame_module, n).detach().contiguous().float()
+    return dict(v_template=g("v_template"), shapedirs=g("shapedirs"), posedirs=g("posedirs"),
+                J_regressor=g("J_regressor"), lbs_weights=g("lbs_weights"),
+                parents=[int(x) for x in flame_module.parents.tolist()])
+
+
+def flame_lbs(model, betas, pose, delta_shapedirs=None, delta_posedirs=None, delta_vertex=None, l0=0, want_orig=True):
+    """model: dict from `model_tensors` (or the same keys built by hand); betas [L] or [1,L]; pose [J*3] or [1,J*3].
+    Returns (verts [1,V,3], pose_feature [1,(J-1)*9], transformations [1,J,4,4]) and, with want_orig, additionally
+    (verts_orig [1,V,3], transformations_orig [1,J,4,4]) -- the same pose without the deltas."""
+    if betas.dim() == 2 and betas.shape[0] != 1:
+        raise FateSplatError("flame_lbs handles one frame per call (the reference's batch size); loop over frames")
+    outs = _FlameLBS.apply(betas, pose, delta_vertex, delta_shapedirs, delta_posedirs, model, int(l0), bool(want_orig))
+    return tuple(o[None] for o in outs)
+
+
+def attach(flame_module):
+    """Rebind `forward_with_delta_blendshape` and `forward` of a reference FLAME module (flame/FLAME.py) to the
+    fused kernels.  model/fateavatar.py:211-222 then runs unchanged: the first call computes both meshes, the
+    second returns the by-product when it is asked for the same (expression, pose) tensors."""
+    model = model_tensors(flame_module)
+    n_shape, n_exp = int(flame_module.n_shape), int(flame_module.n_exp)
+    cache = {}
+
+    def betas_of(expression_params):
+        e = expression_params[:, :n_exp]
+        return torch.cat([torch.zeros(e.shape[0], n_shape, device=e.device, dtype=e.dtype), e], dim=1)
+
+    def key_of(expression_params, full_pose):
+        return (expression_params.data_ptr(), expression_params._version, full_pose.data_ptr(), full_pose._version)
+
+    def forward_with_delta_blendshape(expression_params, full_pose, delta_shapedirs=None, delta_posedirs=None,
+                                      delta_vertex=None):
+        v, pf, A, vo, Ao = flame_lbs(model, betas_of(expression_params), full_pose, delta_shapedirs, delta_posedirs,
+                                     delta_vertex, l0=n_shape, want_orig=True)
+        cache.clear()
+        cache[key_of(expression_params, full_pose)] = (vo, pf, Ao)
+        return v, pf, A
+
+    def forward(expression_params, full_pose):
+        hit = cache.pop(key_of(expression_params, full_pose), None)
+        if hit is not None:
+            return hit
+        v, pf, A = flame_lbs(model, betas_of(expression_params), full_pose, l0=n_shape, want_orig=False)
+        return v, pf, A
+
+    flame_module.forward_with_delta_blendshape = forward_with_delta_blendshape
+    flame_module.forward = forward
+    return flame_module

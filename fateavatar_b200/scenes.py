@@ -200,3 +200,39 @@ def pose_inputs(N=100000, seed=0):
         opacity_raw=rng.standard_normal((N, 1)).astype(np.float32),
         shell_len=0.05,
     )
+
+
+def flame_inputs(seed=0, V=None, n_shape=300, n_exp=100, J=5, with_deltas=True):
+    """Synthetic FLAME-shaped model + one frame's coefficients (SURVEY Appendix C recipe): the licensed FLAME
+    pickle cannot be shipped, so the buffers flame/FLAME.py:72-107 registers are drawn at FLAME's sizes and
+    magnitudes.  V=None uses the 5002-vertex ellipsoid template of `ellipsoid_mesh` (FLAME: 5023)."""
+    rng = np.random.default_rng(seed)
+    if V is None:
+        v_template, _ = ellipsoid_mesh()
+        V = v_template.shape[0]
+    else:
+        d = rng.standard_normal((V, 3))
+        v_template = d / np.linalg.norm(d, axis=1, keepdims=True) * np.array([0.105, 0.155, 0.11])
+    v_template = v_template - v_template.mean(0, keepdims=True)
+    L, NP = n_shape + n_exp, (J - 1) * 9
+    jr = rng.uniform(size=(J, V)) * (rng.uniform(size=(J, V)) < 0.02)
+    jr[:, 0] += 1e-3
+    parents = np.array([-1, 0, 1, 1, 1, 1, 1, 1][:J], np.int64)
+    pose = 0.05 * rng.standard_normal(J * 3)
+    if J >= 3:
+        pose[6] = 0.2  # jaw, cf. canonical_pose in config/fateavatar.yaml
+    betas = np.concatenate([np.zeros(n_shape), 0.5 * rng.standard_normal(n_exp)])
+    out = dict(
+        v_template=v_template, shapedirs=1e-3 * rng.standard_normal((V, 3, L)),
+        posedirs=1e-4 * rng.standard_normal((NP, V * 3)), J_regressor=jr / jr.sum(1, keepdims=True),
+        lbs_weights=np.exp(3.0 * rng.standard_normal((V, J))), parents=parents, betas=betas, pose=pose,
+        n_shape=n_shape, n_exp=n_exp,
+    )
+    out["lbs_weights"] = out["lbs_weights"] / out["lbs_weights"].sum(1, keepdims=True)
+    if with_deltas:
+        out["delta_shapedirs"] = 2e-4 * rng.standard_normal((V, 3, L))
+        out["delta_posedirs"] = 2e-5 * rng.standard_normal((NP, V * 3))
+        out["delta_vertex"] = 1e-3 * rng.standard_normal((V, 3))
+    out = _f32(out)
+    out["parents"] = parents
+    return out

@@ -15,6 +15,7 @@
  *   fs_knn_mean_dist2 <- SimpleKNN::knn  simple-knn/simple_knn.h, simple_knn.cu:186-222; distCUDA2, spatial.cu:15-26
  *   fs_pose_forward / fs_pose_backward <- the per-frame torch ops of model/fateavatar.py:225-258 (no native
  *                        counterpart upstream; see the declaration below)
+ *   fs_flame_forward / fs_flame_backward <- flame/FLAME.py:131-204 + flame/lbs.py:24-100 (torch ops upstream)
  *
  * Differences from the reference native surface, all deliberate:
  *   - plain C, raw device pointers and sizes, explicit stream, no torch/glm/std::function types;
@@ -160,12 +161,46 @@ int fs_pose_backward(int N, int V, int F, const float* d_verts, const long long*
                      float* d_dL_dopacity_raw, void* stream);
 
 /*
+ * FLAME linear blend skinning with personalised blendshape deltas, batch size 1.
+ * Replaces flame/FLAME.py:156-204 (forward_with_delta_blendshape) AND, in the same pass, flame/FLAME.py:131-154
+ * (forward: the same expression/pose without the deltas, FateAvatar's `verts_orig`, model/fateavatar.py:211-222),
+ * i.e. flame/lbs.py:24-100 run twice (no native counterpart upstream: ~40 torch kernels per call).
+ *   betas [L]            shape+expression coefficients (FLAME.py:180: zeros(n_shape) ++ expression)
+ *   l0                   coefficients [0, l0) are KNOWN to be zero (l0 = n_shape upstream): their columns of
+ *                        shapedirs are not read and their gradient rows are written as zeros; pass 0 if unknown
+ *   pose [J*3]           axis-angle per joint;   parents_host [J]: HOST array, parents[0] ignored, parents[j] < j
+ *   v_template [V,3], shapedirs [V,3,L], posedirs [(J-1)*9, V*3], J_regressor [J,V], lbs_weights [V,J]
+ *   delta_vertex [V,3], delta_shapedirs [V,3,L], delta_posedirs [(J-1)*9, V*3]: trainable deltas, each may be NULL
+ * Outputs: verts [V,3]; optional verts_orig [V,3] (no deltas), pose_feature [(J-1)*9], transforms [J,4,4]
+ * (lbs.py "A", relative rigid transforms) for both paths.  The workspace (fs_flame_workspace_bytes, 256-byte
+ * aligned) keeps v_posed, joints and the kinematic chain for fs_flame_backward.
+ * Backward: dL/dverts [V,3] -> dL/d{delta_vertex, delta_shapedirs, delta_posedirs} (each optional), including the
+ * path through the joint regression and the kinematic chain.  d_dL_dv_shaped / d_dL_dv_posed (optional, [V,3])
+ * expose the factors of the two rank-1 gradients (delta_shapedirs grad = dL_dv_shaped (x) betas, delta_posedirs
+ * grad = pose_feature (x) dL_dv_posed) for callers that all-reduce 62 KB instead of 26 MB.
+ * Gradients w.r.t. betas and pose are not produced (FateAvatar does not optimise them on INSTA data).
+ */
+#define FS_FLAME_MAX_JOINTS 8
+size_t fs_flame_workspace_bytes(int V);
+int fs_flame_forward(int V, int L, int l0, int J, const int* parents_host, const float* d_betas, const float* d_pose,
+                     const float* d_v_template, const float* d_delta_vertex, const float* d_shapedirs,
+                     const float* d_delta_shapedirs, const float* d_posedirs, const float* d_delta_posedirs,
+                     const float* d_J_regressor, const float* d_lbs_weights, float* d_verts, float* d_verts_orig,
+                     float* d_pose_feature, float* d_transforms, float* d_transforms_orig, void* d_workspace,
+                     size_t workspace_bytes, void* stream);
+int fs_flame_backward(int V, int L, int l0, int J, const int* parents_host, const float* d_betas,
+                      const float* d_J_regressor, const float* d_lbs_weights, const float* d_dL_dverts,
+                      void* d_workspace, size_t workspace_bytes, float* d_dL_ddelta_vertex,
+                      float* d_dL_ddelta_shapedirs, float* d_dL_ddelta_posedirs, float* d_dL_dv_shaped,
+                      float* d_dL_dv_posed, void* stream);
+
+/*
  * Optional per-stage device timing for bench.py's roofline figures.  While enabled, every stage launch is
  * bracketed by CUDA events on the launching stream; fs_profile_read waits for them and returns, per stage id
  * (0 preprocess, 1 tile_scan, 2 scatter, 3 tile_sort, 4 big_tile_sort, 5 blend_forward, 6 blend_backward,
- * 7 preprocess_backward, 8 knn, 9 pose_forward, 10 pose_backward), the summed milliseconds and the number of launches since the last read.
+ * 7 preprocess_backward, 8 knn, 9 pose_forward, 10 pose_backward, 11 flame_forward, 12 flame_backward), the summed milliseconds and the number of launches since the last read.
  */
-#define FS_NUM_STAGES 11
+#define FS_NUM_STAGES 13
 void fs_profile_enable(int on);
 int fs_profile_read(float* total_ms, int* counts, int n);
 

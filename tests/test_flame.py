@@ -1,0 +1,203 @@
+"""FLAME skinning stage: the oracle is pinned against the reference's own flame/lbs.py (when the
+tree is mounted) and against the committed fixture made from it; the fused kernels are compared with the oracle's
+float64 forward / autograd backward and with the fixture, through the C ABI."""
+import ctypes as C
+import importlib.util
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from fateavatar_b200 import _lib, scenes
+from oracle import flame_oracle as fo
+
+REF_LBS = "/root/reference/flame/lbs.py"
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "flame_small.npz")
+GOLDEN_CASE = dict(seed=21, V=150)  # tests/golden/make_flame_golden.py
+DELTAS = ("delta_vertex", "delta_shapedirs", "delta_posedirs")
+
+
+def _model(f, dtype, device="cpu"):
+    m = {k: torch.from_numpy(f[k]).to(dtype).to(device) for k in ("v_template", "shapedirs", "posedirs", "J_regressor", "lbs_weights")}
+    m["parents"] = torch.from_numpy(f["parents"])
+    return m
+
+
+def oracle_run(f, dtype=torch.float64, upstream=None, deltas=True):
+    m = _model(f, dtype)
+    t = lambda k: torch.from_numpy(f[k]).to(dtype)
+    leaves = {k: t(k).requires_grad_(True) for k in DELTAS} if deltas else {}
+    verts, pf, A = fo.forward_with_delta_blendshape(m, t("betas"), t("pose"), leaves.get("delta_shapedirs"),
+                                                    leaves.get("delta_posedirs"), leaves.get("delta_vertex"))
+    res = dict(verts=verts.detach().numpy(), pose_feature=pf.detach().numpy(), A=A.detach().numpy())
+    if upstream is not None:
+        (verts * torch.from_numpy(upstream).to(dtype)).sum().backward()
+        res["grads"] = {k: leaves[k].grad.numpy() for k in DELTAS}
+    return res
+
+
+# ---------------------------------------------------------------------------------------------- CPU: the oracle
+@pytest.mark.skipif(not os.path.exists(REF_LBS), reason="reference tree not mounted")
+@pytest.mark.parametrize("deltas", [True, False])
+def test_oracle_matches_reference_lbs_file(deltas):
+    spec = importlib.util.spec_from_file_location("ref_flame_lbs", REF_LBS)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    f = scenes.flame_inputs(seed=3, V=97)
+    t = lambda k: torch.from_numpy(f[k]).double()
+    leaves = [t(k).requires_grad_(True) for k in DELTAS] if deltas else [None] * 3
+    vt = t("v_template")[None] + (leaves[0][None] if deltas else 0)
+    sd = t("shapedirs") + (leaves[1] if deltas else 0)
+    pd = t("posedirs") + (leaves[2] if deltas else 0)
+    v, pf, A = ref.lbs(t("betas")[None], t("pose")[None], vt, sd, pd, t("J_regressor"), torch.from_numpy(f["parents"]),
+                       t("lbs_weights"), dtype=torch.float64)
+    g = np.random.default_rng(0).standard_normal((97, 3))
+    o = oracle_run(f, torch.float64, upstream=g if deltas else None, deltas=deltas)
+    np.testing.assert_allclose(o["verts"], v[0].detach().numpy(), rtol=0, atol=1e-13)
+    np.testing.assert_allclose(o["pose_feature"], pf[0].detach().numpy(), rtol=0, atol=1e-14)
+    np.testing.assert_allclose(o["A"], A[0].detach().numpy(), rtol=0, atol=1e-13)
+    if deltas:
+        (v[0] * torch.from_numpy(g)).sum().backward()
+        for k, leaf in zip(DELTAS, leaves):
+            np.testing.assert_allclose(o["grads"][k], leaf.grad.numpy(), rtol=0, atol=1e-12 * max(1.0, float(leaf.grad.abs().max())))
+
+
+def test_oracle_matches_golden_fixture_from_reference():
+    gold = np.load(GOLDEN)
+    f = scenes.flame_inputs(**GOLDEN_CASE)
+    g = np.random.default_rng(5).standard_normal((GOLDEN_CASE["V"], 3)).astype(np.float32)
+    o = oracle_run(f, torch.float64, upstream=g)
+    np.testing.assert_allclose(o["verts"], gold["verts"], rtol=0, atol=2e-7)       # fixture forward is fp32
+    np.testing.assert_allclose(o["pose_feature"], gold["pose_feature"], rtol=0, atol=2e-7)
+    np.testing.assert_allclose(o["A"], gold["A"], rtol=0, atol=2e-7)
+    o0 = oracle_run(f, torch.float64, deltas=False)
+    np.testing.assert_allclose(o0["verts"], gold["verts_orig"], rtol=0, atol=2e-7)
+    np.testing.assert_allclose(o0["A"], gold["A_orig"], rtol=0, atol=2e-7)
+    for k in DELTAS:
+        ref = gold["d_" + k]
+        np.testing.assert_allclose(o["grads"][k], ref, rtol=0, atol=2e-7 * max(1.0, float(np.abs(ref).max())))
+
+
+def test_flame_abi_rejects_bad_arguments_without_touching_the_gpu():
+    lib = _lib.load()
+    bad_tree = (C.c_int * 5)(-1, 0, 3, 1, 1)  # parents[2] = 3 is not < 2
+    ok_tree = (C.c_int * 5)(-1, 0, 1, 1, 1)
+    nul = [None] * 10 + [None] * 5
+    assert lib.fs_flame_forward(10, 8, 0, 5, bad_tree, *nul, None, 0, None) == -1
+    assert b"kinematic" in lib.fs_last_error()
+    assert lib.fs_flame_forward(0, 8, 0, 5, ok_tree, *nul, None, 0, None) == -1
+    assert lib.fs_flame_forward(10, 8, 9, 5, ok_tree, *nul, None, 0, None) == -1          # l0 > L
+    assert lib.fs_flame_forward(10, 8, 0, 9, ok_tree, *nul, None, 0, None) == -1          # J > FS_FLAME_MAX_JOINTS
+    assert lib.fs_flame_backward(10, 8, 0, 5, bad_tree, None, None, None, None, None, 0, None, None, None, None, None, None) == -1
+    assert lib.fs_flame_workspace_bytes(0) == 0
+
+
+# ---------------------------------------------------------------------------------------------- GPU: the kernels
+def _run_gpu(f, dev, l0, deltas=True, upstream=None, want_orig=True):
+    from fateavatar_b200 import flame
+
+    m = _model(f, torch.float32, dev)
+    m["parents"] = [int(x) for x in f["parents"]]
+    t = lambda k: torch.from_numpy(f[k]).to(dev)
+    leaves = {k: t(k).requires_grad_(True) for k in DELTAS} if deltas else {}
+    outs = flame.flame_lbs(m, t("betas")[None], t("pose")[None], leaves.get("delta_shapedirs"), leaves.get("delta_posedirs"),
+                           leaves.get("delta_vertex"), l0=l0, want_orig=want_orig)
+    res = dict(verts=outs[0][0].detach().cpu().numpy(), pose_feature=outs[1][0].cpu().numpy(), A=outs[2][0].cpu().numpy())
+    if want_orig:
+        res.update(verts_orig=outs[3][0].cpu().numpy(), A_orig=outs[4][0].cpu().numpy())
+    if upstream is not None:
+        (outs[0][0] * torch.from_numpy(upstream).to(dev)).sum().backward()
+        res["grads"] = {k: leaves[k].grad.cpu().numpy() for k in DELTAS}
+    torch.cuda.synchronize()
+    return res
+
+
+def _check(got, o, o0, atol_v=1e-6):
+    # tolerance: fp32 sums of <= 400 + 36 + 5 terms in a different order than cuBLAS's; vertices are ~0.15 in size
+    assert np.abs(got["verts"] - o["verts"]).max() <= atol_v
+    assert np.abs(got["pose_feature"] - o["pose_feature"]).max() <= 2e-7
+    assert np.abs(got["A"] - o["A"]).max() <= 1e-6
+    if o0 is not None:
+        assert np.abs(got["verts_orig"] - o0["verts"]).max() <= atol_v
+        assert np.abs(got["A_orig"] - o0["A"]).max() <= 1e-6
+    if "grads" in got:
+        for k in DELTAS:
+            ref = o["grads"][k]
+            err = np.abs(got["grads"][k] - ref).max()
+            assert err <= 1e-5 * max(float(np.abs(ref).max()), 1e-12), (k, err, np.abs(ref).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["golden_150", "flame_size_5002", "ragged_v_33"])
+def test_flame_kernels_vs_oracle(case, cuda_device):
+    f = {"golden_150": lambda: scenes.flame_inputs(**GOLDEN_CASE), "flame_size_5002": lambda: scenes.flame_inputs(seed=1),
+         "ragged_v_33": lambda: scenes.flame_inputs(seed=2, V=33)}[case]()
+    V = f["v_template"].shape[0]
+    g = np.random.default_rng(5).standard_normal((V, 3)).astype(np.float32)
+    got = _run_gpu(f, cuda_device, l0=f["n_shape"], upstream=g)
+    _check(got, oracle_run(f, upstream=g), oracle_run(f, deltas=False))
+    # structural zeros: coefficients below l0 never receive gradient
+    assert not got["grads"]["delta_shapedirs"][:, :, : f["n_shape"]].any()
+    if case == "golden_150":
+        gold = np.load(GOLDEN)
+        assert np.abs(got["verts"] - gold["verts"]).max() <= 1e-6
+        assert np.abs(got["verts_orig"] - gold["verts_orig"]).max() <= 1e-6
+        for k in DELTAS:
+            ref = gold["d_" + k]
+            assert np.abs(got["grads"][k] - ref).max() <= 1e-5 * float(np.abs(ref).max())
+
+
+@pytest.mark.gpu
+def test_flame_variants_no_deltas_dense_betas_scalar_path_three_joints(cuda_device):
+    # no deltas at all (FLAME.forward), verts_orig not requested
+    f = scenes.flame_inputs(seed=4, V=77, with_deltas=False)
+    got = _run_gpu(f, cuda_device, l0=f["n_shape"], deltas=False, want_orig=False)
+    _check(got, oracle_run(f, deltas=False), None)
+    # shape coefficients non-zero, l0 = 0 (every column read)
+    f = scenes.flame_inputs(seed=5, V=64)
+    f["betas"][:300] = 0.3 * np.random.default_rng(1).standard_normal(300).astype(np.float32)
+    g = np.random.default_rng(6).standard_normal((64, 3)).astype(np.float32)
+    _check(_run_gpu(f, cuda_device, l0=0, upstream=g), oracle_run(f, upstream=g), oracle_run(f, deltas=False))
+    # coefficient counts that are not multiples of 4 (scalar load path) and a 3-joint tree
+    f = scenes.flame_inputs(seed=6, V=50, n_shape=7, n_exp=11, J=3)
+    g = np.random.default_rng(7).standard_normal((50, 3)).astype(np.float32)
+    _check(_run_gpu(f, cuda_device, l0=7, upstream=g), oracle_run(f, upstream=g), oracle_run(f, deltas=False))
+
+
+@pytest.mark.gpu
+def test_attach_rebinds_reference_flame_module_methods(cuda_device):
+    """The two calls of model/fateavatar.py:211-222 on a FLAME-module look-alike: same results as the oracle,
+    second call served from the first, gradients reach the delta parameters, expression grads refuse loudly."""
+    from fateavatar_b200 import flame
+    from fateavatar_b200._lib import FateSplatError
+
+    f = scenes.flame_inputs(seed=8, V=120)
+    mod = types.SimpleNamespace(n_shape=f["n_shape"], n_exp=f["n_exp"], parents=torch.from_numpy(f["parents"]))
+    for k in ("v_template", "shapedirs", "posedirs", "J_regressor", "lbs_weights"):
+        setattr(mod, k, torch.from_numpy(f[k]).to(cuda_device))
+    flame.attach(mod)
+    expr = torch.from_numpy(f["betas"][300:])[None].to(cuda_device)
+    pose = torch.from_numpy(f["pose"])[None].to(cuda_device)
+    leaves = {k: torch.from_numpy(f[k]).to(cuda_device).requires_grad_(True) for k in DELTAS}
+    verts, pf, A = mod.forward_with_delta_blendshape(expression_params=expr, full_pose=pose, delta_shapedirs=leaves["delta_shapedirs"],
+                                                     delta_posedirs=leaves["delta_posedirs"], delta_vertex=leaves["delta_vertex"])
+    lc0 = _lib.load().fs_last_launch_count()
+    verts_orig, _, _ = mod.forward(expression_params=expr, full_pose=pose)
+    assert verts.shape == (1, 120, 3) and pf.shape == (1, 36) and A.shape == (1, 5, 4, 4) and verts_orig.shape == (1, 120, 3)
+    g = np.random.default_rng(9).standard_normal((120, 3)).astype(np.float32)
+    o, o0 = oracle_run(f, upstream=g), oracle_run(f, deltas=False)
+    assert np.abs(verts[0].detach().cpu().numpy() - o["verts"]).max() <= 1e-6
+    assert np.abs(verts_orig[0].cpu().numpy() - o0["verts"]).max() <= 1e-6
+    ((verts[0] - verts_orig[0]) * torch.from_numpy(g).to(cuda_device)).sum().backward()  # mesh-loss style use of both
+    for k in DELTAS:
+        ref = o["grads"][k]
+        assert np.abs(leaves[k].grad.cpu().numpy() - ref).max() <= 1e-5 * float(np.abs(ref).max())
+    # a different pose is not served from the cache
+    v2, _, _ = mod.forward(expression_params=expr, full_pose=pose * 0.5)
+    assert np.abs(v2[0].cpu().numpy() - o0["verts"]).max() > 1e-5
+    with pytest.raises(FateSplatError):
+        mod.forward_with_delta_blendshape(expr.clone().requires_grad_(True), pose, leaves["delta_shapedirs"], leaves["delta_posedirs"],
+                                          leaves["delta_vertex"])
+    assert lc0 >= 2
