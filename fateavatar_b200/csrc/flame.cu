@@ -28,8 +28,11 @@
 namespace {
 
 constexpr int kMaxJ = FS_FLAME_MAX_JOINTS;
-constexpr int kBlendThreads = 512;                  // 16 warps, one vertex per warp per iteration
-constexpr int kSkinVerts = 32, kSkinThreads = 96;   // a skin CTA owns 32 vertices = 96 coordinates
+constexpr int kBlendThreads = 1024;                 // forward: 32 warps per SM, one vertex per warp per iteration
+constexpr int kBlendBwdThreads = 512;
+constexpr int kSkinVerts = 32, kSkinCoords = 96;  // a skin CTA owns 32 vertices = 96 coordinates
+constexpr int kSkinThreads = 256;                 // 2 x 96 split the pose-corrective sum, the rest help the prologue
+constexpr int kSkinBwdThreads = 96;
 
 struct Parents {
     int p[kMaxJ];
@@ -79,6 +82,26 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Sum of `n` per-CTA partials of one slot, laid out [slot][n]: 8 consecutive threads share a slot, every load is
+// independent (one memory round trip), fixed order => deterministic.  Valid in all 8 threads.
+__device__ __forceinline__ float reduce_partials8(const float* __restrict__ part, int slot, int n, int stride, int sub) {
+    float s = 0.f;
+    for (int b0 = 0; b0 < n; b0 += 8 * 24) {  // one pass for up to 192 producer CTAs
+        float v[24];
+#pragma unroll
+        for (int i = 0; i < 24; ++i) {
+            const int b = b0 + sub + 8 * i;
+            v[i] = b < n ? part[(size_t)slot * stride + b] : 0.0f;
+        }
+#pragma unroll
+        for (int i = 0; i < 24; ++i) s += v[i];
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    return s;
+}
+
 // ---- forward 1: blendshapes ------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlendThreads)
 flame_blend_kernel(int V, int L, int l0, int J, const float* __restrict__ betas, const float* __restrict__ v_template,
@@ -92,39 +115,55 @@ flame_blend_kernel(int V, int L, int l0, int J, const float* __restrict__ betas,
     const bool vec = ((L | l0) & 3) == 0;  // rows start 16-byte aligned and hold whole float4s
     const int nslot = 2 * J * 3;
     float jp0 = 0.f, jp1 = 0.f;  // joint partial sums of slots lane, lane + 32
+    fs::pdl_trigger();  // the skin kernel may start its own prologue (rotations, pose correctives) right away
 
     for (int v = blockIdx.x * (kBlendThreads / 32) + wid; v < V; v += nw) {
-        float ao[3] = {0.f, 0.f, 0.f}, ad[3] = {0.f, 0.f, 0.f};  // sum beta * S, sum beta * (S + dS)
+        float jw[2];  // this lane's joint-regressor weights, requested together with the blendshape rows
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const size_t row = ((size_t)v * 3 + k) * L + l0;
-            if (vec) {
-                const float4* s4 = reinterpret_cast<const float4*>(shapedirs + row);
-                const float4* d4 = delta_shapedirs ? reinterpret_cast<const float4*>(delta_shapedirs + row) : nullptr;
-                const float4* b4 = reinterpret_cast<const float4*>(betas + l0);
-                for (int c = lane; c < (n >> 2); c += 32) {
-                    const float4 s = __ldg(s4 + c), b = __ldg(b4 + c);
-                    ao[k] += b.x * s.x + b.y * s.y + b.z * s.z + b.w * s.w;
-                    if (d4) {
-                        const float4 d = __ldg(d4 + c);
-                        ad[k] += b.x * (s.x + d.x) + b.y * (s.y + d.y) + b.z * (s.z + d.z) + b.w * (s.w + d.w);
-                    }
+        for (int h = 0; h < 2; ++h) {
+            const int slot = lane + 32 * h;
+            jw[h] = slot < nslot ? __ldg(J_regressor + (size_t)((slot % (3 * J)) / 3) * V + v) : 0.0f;
+        }
+        float ao[3] = {0.f, 0.f, 0.f}, ad[3] = {0.f, 0.f, 0.f};  // sum beta * S, sum beta * (S + dS)
+        const size_t row0 = (size_t)v * 3 * L + l0;
+        if (vec) {  // the three rows of a vertex are requested together: one memory round trip per 32 float4 columns
+            const float4* b4 = reinterpret_cast<const float4*>(betas + l0);
+            for (int c = lane; c < (n >> 2); c += 32) {
+                float4 sv[3], dv[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    sv[k] = __ldg(reinterpret_cast<const float4*>(shapedirs + row0 + (size_t)k * L) + c);
+                    dv[k] = delta_shapedirs ? __ldg(reinterpret_cast<const float4*>(delta_shapedirs + row0 + (size_t)k * L) + c)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-            } else {
-                for (int c = lane; c < n; c += 32) {
-                    const float s = __ldg(shapedirs + row + c), b = __ldg(betas + l0 + c);
-                    ao[k] += b * s;
-                    if (delta_shapedirs) ad[k] += b * (s + __ldg(delta_shapedirs + row + c));
+                const float4 b = __ldg(b4 + c);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    ao[k] += b.x * sv[k].x + b.y * sv[k].y + b.z * sv[k].z + b.w * sv[k].w;
+                    ad[k] += b.x * (sv[k].x + dv[k].x) + b.y * (sv[k].y + dv[k].y) + b.z * (sv[k].z + dv[k].z) +
+                             b.w * (sv[k].w + dv[k].w);
+                }
+            }
+        } else {
+            for (int c = lane; c < n; c += 32) {
+                const float b = __ldg(betas + l0 + c);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float sv = __ldg(shapedirs + row0 + (size_t)k * L + c);
+                    ao[k] += b * sv;
+                    if (delta_shapedirs) ad[k] += b * (sv + __ldg(delta_shapedirs + row0 + (size_t)k * L + c));
                 }
             }
         }
+        const float tv = lane < 3 ? __ldg(v_template + 3 * v + lane) : 0.0f;
+        const float dvv = (delta_vertex && lane < 3) ? __ldg(delta_vertex + 3 * v + lane) : 0.0f;
         float vs[2][3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const float so = warp_sum(ao[k]);
             const float sd = delta_shapedirs ? warp_sum(ad[k]) : so;
-            const float t = __ldg(v_template + 3 * v + k);
-            vs[0][k] = (delta_vertex ? t + __ldg(delta_vertex + 3 * v + k) : t) + sd;
+            const float t = __shfl_sync(0xffffffffu, tv, k), dd = __shfl_sync(0xffffffffu, dvv, k);
+            vs[0][k] = (delta_vertex ? t + dd : t) + sd;
             vs[1][k] = t + so;
         }
         if (lane < 6) {
@@ -137,11 +176,10 @@ flame_blend_kernel(int V, int L, int l0, int J, const float* __restrict__ betas,
         for (int h = 0; h < 2; ++h) {
             const int slot = lane + 32 * h;
             if (slot < nslot) {
-                const int path = slot / (3 * J), r = slot % (3 * J), j = r / 3, k = r % 3;
+                const int path = slot / (3 * J), k = (slot % (3 * J)) % 3;
                 const float a = path ? (k == 0 ? vs[1][0] : k == 1 ? vs[1][1] : vs[1][2])
                                      : (k == 0 ? vs[0][0] : k == 1 ? vs[0][1] : vs[0][2]);
-                const float w = __ldg(J_regressor + (size_t)j * V + v);
-                if (h == 0) jp0 += w * a; else jp1 += w * a;
+                if (h == 0) jp0 += jw[0] * a; else jp1 += jw[1] * a;
             }
         }
     }
@@ -154,7 +192,6 @@ flame_blend_kernel(int V, int L, int l0, int J, const float* __restrict__ betas,
         for (int w = 0; w < kBlendThreads / 32; ++w) s += s_j[w][threadIdx.x];
         jpart[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = s;  // [slot][CTA]: the consumer reads along CTAs
     }
-    fs::pdl_trigger();
 }
 
 // Rodrigues exactly as lbs.py:253-270: angle = ||r + 1e-8||, K from r / angle, R = I + sin K + (1 - cos) K K.
@@ -182,27 +219,48 @@ flame_skin_kernel(int V, int J, Parents parents, int nblk_blend, const float* __
                   float* __restrict__ verts, float* __restrict__ verts_orig, float* __restrict__ pose_feature_out,
                   float* __restrict__ transforms, float* __restrict__ transforms_orig) {
     __shared__ FlameState S;
-    __shared__ float s_vp[2][kSkinThreads];
+    __shared__ float s_vp[2][kSkinCoords], s_po[2][kSkinCoords], s_pd[2][kSkinCoords];
     const int t = threadIdx.x;
-    const int NP = (J - 1) * 9;
-    // rotations do not depend on the previous kernel: compute them before waiting for it
-    if (t >= 64 && t < 64 + J) {
-        const int j = t - 64;
+    const int NP = (J - 1) * 9, n3 = 3 * V;
+    // ---- everything that does not depend on the blend kernel runs before the wait and overlaps it -------------
+    if (t >= 192 && t < 192 + J) {
+        const int j = t - 192;
         const float r[3] = {__ldg(pose + 3 * j), __ldg(pose + 3 * j + 1), __ldg(pose + 3 * j + 2)};
         rodrigues(r, S.R[j]);
         if (j > 0)
 #pragma unroll
             for (int e = 0; e < 9; ++e) S.pf[(j - 1) * 9 + e] = S.R[j][e] - ((e % 4) == 0 ? 1.0f : 0.0f);
     }
-    fs::pdl_wait();
-    {   // finish the joint regression: one warp per slot, lanes along the producer CTAs, fixed order
-        const int lane = t & 31, wid = t >> 5;
-        for (int slot = wid; slot < 2 * J * 3; slot += kSkinThreads / 32) {
-            float s = 0.f;
-            for (int b = lane; b < nblk_blend; b += 32) s += jpart[(size_t)slot * nblk_blend + b];
-            s = warp_sum(s);
-            if (lane == 0) (&S.J[0][0][0])[(slot / (3 * J)) * kMaxJ * 3 + (slot % (3 * J))] = s;
+    __syncthreads();
+    const int tc = t % kSkinCoords, part = t / kSkinCoords;  // part 0/1: even/odd rows of posedirs; 2: helpers
+    const int e = blockIdx.x * kSkinCoords + tc;             // coordinate index 3 v + k
+    float wj[kMaxJ];
+    if (part < 2 && e < n3) {
+        float po = 0.f, pd = 0.f;  // pose_feature @ posedirs, pose_feature @ (posedirs + delta)
+#pragma unroll 6
+        for (int i = part; i < NP; i += 2) {
+            const float p = __ldg(posedirs + (size_t)i * n3 + e);
+            po += S.pf[i] * p;
+            if (delta_posedirs) pd += S.pf[i] * (p + __ldg(delta_posedirs + (size_t)i * n3 + e));
         }
+        s_po[part][tc] = po;
+        s_pd[part][tc] = delta_posedirs ? pd : po;
+        if (part == 0)
+#pragma unroll
+            for (int j = 0; j < kMaxJ; ++j) wj[j] = j < J ? __ldg(lbs_weights + (size_t)(e / 3) * J + j) : 0.0f;
+    }
+    fs::pdl_wait();
+    float vsd = 0.f, vso = 0.f;
+    if (part == 0 && e < n3) {
+        vsd = v_shaped[e];
+        vso = v_shaped[(size_t)n3 + e];
+    }
+    // finish the joint regression (lbs.py:207)
+    for (int base = 0; base < 2 * J * 3; base += kSkinThreads / 8) {  // warp-uniform trip count (shuffles inside)
+        const int slot = base + (t >> 3);
+        const bool live = slot < 2 * J * 3;
+        const float sum = reduce_partials8(jpart, live ? slot : 0, live ? nblk_blend : 0, nblk_blend, t & 7);
+        if (live && (t & 7) == 0) (&S.J[0][0][0])[(slot / (3 * J)) * kMaxJ * 3 + (slot % (3 * J))] = sum;
     }
     __syncthreads();
     if (t < 64) {  // kinematic chain (lbs.py:285-342): warp p_ = path, lanes 0..8 = rotation entries, 9..11 = translation
@@ -248,33 +306,28 @@ flame_skin_kernel(int V, int J, Parents parents, int nblk_blend, const float* __
         }
     }
 
-    const int e = blockIdx.x * kSkinThreads + t;  // coordinate index 3 v + k
-    const int n3 = 3 * V;
-    float vpd = 0.f, vpo = 0.f;
-    if (e < n3) {
-        float po = 0.f, pd = 0.f;  // pose_feature @ posedirs, pose_feature @ (posedirs + delta)
-        for (int i = 0; i < NP; ++i) {
-            const float p = __ldg(posedirs + (size_t)i * n3 + e);
-            po += S.pf[i] * p;
-            if (delta_posedirs) pd += S.pf[i] * (p + __ldg(delta_posedirs + (size_t)i * n3 + e));
+    if (part == 0) {
+        float vpd = 0.f, vpo = 0.f;
+        if (e < n3) {
+            vpd = (s_pd[0][tc] + s_pd[1][tc]) + vsd;
+            vpo = (s_po[0][tc] + s_po[1][tc]) + vso;
+            v_posed_out[e] = vpd;
         }
-        if (!delta_posedirs) pd = po;
-        vpd = pd + v_shaped[e];
-        vpo = po + v_shaped[(size_t)n3 + e];
-        v_posed_out[e] = vpd;
+        s_vp[0][tc] = vpd;
+        s_vp[1][tc] = vpo;
     }
-    s_vp[0][t] = vpd;
-    s_vp[1][t] = vpo;
     __syncthreads();
-    if (e < n3) {
-        const int vl = t / 3, k = t % 3, v = e / 3;
+    if (part == 0 && e < n3) {
+        const int vl = tc / 3, k = tc % 3;
         float Td[4] = {0.f, 0.f, 0.f, 0.f}, To[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int j = 0; j < J; ++j) {
-            const float w = __ldg(lbs_weights + (size_t)v * J + j);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                Td[c] += w * S.A[0][j][k * 4 + c];
-                To[c] += w * S.A[1][j][k * 4 + c];
+        for (int j = 0; j < kMaxJ; ++j) {
+            if (j < J) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    Td[c] += wj[j] * S.A[0][j][k * 4 + c];
+                    To[c] += wj[j] * S.A[1][j][k * 4 + c];
+                }
             }
         }
         verts[e] = Td[0] * s_vp[0][3 * vl] + Td[1] * s_vp[0][3 * vl + 1] + Td[2] * s_vp[0][3 * vl + 2] + Td[3];
@@ -284,19 +337,19 @@ flame_skin_kernel(int V, int J, Parents parents, int nblk_blend, const float* __
 }
 
 // ---- backward 1: through the skinning ----------------------------------------------------------------------
-__global__ void __launch_bounds__(kSkinThreads)
+__global__ void __launch_bounds__(kSkinBwdThreads)
 flame_skin_backward_kernel(int V, int J, const float* __restrict__ lbs_weights, const FlameState* __restrict__ state,
                            const float* __restrict__ v_posed, const float* __restrict__ dL_dverts,
                            float* __restrict__ g_posed, float* __restrict__ dapart /*[12J][grid]*/) {
     __shared__ float s_A[kMaxJ][12];
-    __shared__ float s_g[kSkinThreads], s_vp[kSkinThreads], s_w[kSkinVerts][kMaxJ];
+    __shared__ float s_g[kSkinBwdThreads], s_vp[kSkinBwdThreads], s_w[kSkinVerts][kMaxJ];
     const int t = threadIdx.x;
     const int v0 = blockIdx.x * kSkinVerts;
-    const int e = blockIdx.x * kSkinThreads + t, n3 = 3 * V;
-    for (int i = t; i < J * 12; i += kSkinThreads) s_A[i / 12][i % 12] = state->A[0][i / 12][i % 12];
+    const int e = blockIdx.x * kSkinBwdThreads + t, n3 = 3 * V;
+    for (int i = t; i < J * 12; i += kSkinBwdThreads) s_A[i / 12][i % 12] = state->A[0][i / 12][i % 12];
     s_g[t] = e < n3 ? dL_dverts[e] : 0.0f;
     s_vp[t] = e < n3 ? v_posed[e] : 0.0f;
-    for (int i = t; i < kSkinVerts * J; i += kSkinThreads) {
+    for (int i = t; i < kSkinVerts * J; i += kSkinBwdThreads) {
         const int vl = i / J, j = i % J;
         s_w[vl][j] = (v0 + vl) < V ? __ldg(lbs_weights + (size_t)(v0 + vl) * J + j) : 0.0f;
     }
@@ -323,7 +376,7 @@ flame_skin_backward_kernel(int V, int J, const float* __restrict__ lbs_weights, 
 }
 
 // ---- backward 2: chain backward + parameter gradients -------------------------------------------------------
-__global__ void __launch_bounds__(kBlendThreads)
+__global__ void __launch_bounds__(kBlendBwdThreads)
 flame_blend_backward_kernel(int V, int L, int l0, int J, Parents parents, int nblk_skin,
                             const float* __restrict__ betas, const float* __restrict__ J_regressor,
                             const FlameState* __restrict__ state, const float* __restrict__ g_posed,
@@ -332,30 +385,31 @@ flame_blend_backward_kernel(int V, int L, int l0, int J, Parents parents, int nb
                             float* __restrict__ d_v_shaped) {
     __shared__ float s_dA[kMaxJ][12];
     __shared__ float s_dJ[kMaxJ][3], s_dRg[kMaxJ][9], s_dtg[kMaxJ][3];
-    __shared__ float s_pf[(kMaxJ - 1) * 9];
+    __shared__ FlameState S;  // forward state (joints, rotations, chain): one round trip instead of one per use
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const int NP = (J - 1) * 9, n3 = 3 * V;
+    for (int i = t; i < (int)(sizeof(FlameState) / sizeof(float)); i += kBlendBwdThreads)
+        reinterpret_cast<float*>(&S)[i] = reinterpret_cast<const float*>(state)[i];  // written by the forward call
     fs::pdl_wait();
-    for (int slot = wid; slot < J * 12; slot += kBlendThreads / 32) {  // lanes along the producer CTAs, fixed order
-        float s = 0.f;
-        for (int b = lane; b < nblk_skin; b += 32) s += dapart[(size_t)slot * nblk_skin + b];
-        s = warp_sum(s);
-        if (lane == 0) s_dA[slot / 12][slot % 12] = s;
+    for (int base = 0; base < J * 12; base += kBlendBwdThreads / 8) {  // warp-uniform trip count (shuffles inside)
+        const int slot = base + (t >> 3);
+        const bool live = slot < J * 12;
+        const float sum = reduce_partials8(dapart, live ? slot : 0, live ? nblk_skin : 0, nblk_skin, t & 7);
+        if (live && (t & 7) == 0) s_dA[slot / 12][slot % 12] = sum;
     }
-    if (t >= 128 && t < 128 + NP) s_pf[t - 128] = state->pf[t - 128];
     __syncthreads();
     if (wid == 0) {
         // A[j] = [Rg_j | tg_j - Rg_j J_j];  Rg_j = Rg_p R_j;  tg_j = Rg_p (J_j - J_p) + tg_p  (j > 0);  tg_0 = J_0
         // lanes 0..8 own the entries of dRg, 9..11 those of drel / dJ, 12..14 those of dtg
         for (int i = lane; i < J * 12; i += 32) {
             const int j = i / 12, r = i % 12;
-            if (r < 9) s_dRg[j][r] = s_dA[j][(r / 3) * 4 + r % 3] - s_dA[j][(r / 3) * 4 + 3] * state->J[0][j][r % 3];
+            if (r < 9) s_dRg[j][r] = s_dA[j][(r / 3) * 4 + r % 3] - s_dA[j][(r / 3) * 4 + 3] * S.J[0][j][r % 3];
             else s_dtg[j][r - 9] = s_dA[j][(r - 9) * 4 + 3];
         }
         __syncwarp();
         for (int i = lane; i < J * 3; i += 32) {
             const int j = i / 3, b = i % 3;
-            const float* G = state->Rg[0][j];
+            const float* G = S.Rg[0][j];
             s_dJ[j][b] = -(G[b] * s_dtg[j][0] + G[3 + b] * s_dtg[j][1] + G[6 + b] * s_dtg[j][2]);
         }
         __syncwarp();
@@ -363,13 +417,13 @@ flame_blend_backward_kernel(int V, int L, int l0, int J, Parents parents, int nb
             const int pa = parents.p[j];
             if (lane < 9) {  // dRg_p += dRg_j R_j^T + dtg_j (x) rel
                 const int a = lane / 3, b = lane % 3;
-                const float* Rj = state->R[j];
-                const float rel = state->J[0][j][b] - state->J[0][pa][b];
+                const float* Rj = S.R[j];
+                const float rel = S.J[0][j][b] - S.J[0][pa][b];
                 s_dRg[pa][lane] += s_dRg[j][a * 3] * Rj[b * 3] + s_dRg[j][a * 3 + 1] * Rj[b * 3 + 1] +
                                    s_dRg[j][a * 3 + 2] * Rj[b * 3 + 2] + s_dtg[j][a] * rel;
             } else if (lane < 12) {  // drel = Rg_p^T dtg_j
                 const int b = lane - 9;
-                const float* Gp = state->Rg[0][pa];
+                const float* Gp = S.Rg[0][pa];
                 const float drel = Gp[b] * s_dtg[j][0] + Gp[3 + b] * s_dtg[j][1] + Gp[6 + b] * s_dtg[j][2];
                 s_dJ[j][b] += drel;
                 s_dJ[pa][b] -= drel;
@@ -384,37 +438,51 @@ flame_blend_backward_kernel(int V, int L, int l0, int J, Parents parents, int nb
 
     // rank-1 gradient of delta_posedirs: pose_feature (x) dL/dv_posed, coalesced along the coordinate axis
     if (d_delta_posedirs) {
-        const int nthreads = gridDim.x * kBlendThreads;
-        for (int e = blockIdx.x * kBlendThreads + t; e < n3; e += nthreads) {
+        const int nthreads = gridDim.x * kBlendBwdThreads;
+        for (int e = blockIdx.x * kBlendBwdThreads + t; e < n3; e += nthreads) {
             const float g = g_posed[e];
-            for (int i = 0; i < NP; ++i) __stcs(d_delta_posedirs + (size_t)i * n3 + e, s_pf[i] * g);
+            for (int i = 0; i < NP; ++i) __stcs(d_delta_posedirs + (size_t)i * n3 + e, S.pf[i] * g);
         }
     }
-    // per coordinate row: dL/dv_shaped, delta_vertex, and the rank-1 gradient of delta_shapedirs
-    const int nw = gridDim.x * (kBlendThreads / 32);
+    // per coordinate row: dL/dv_shaped, delta_vertex, and the rank-1 gradient of delta_shapedirs.  A warp owns rows
+    // w, w + nw, ...; lane i first computes row i's scalar (all loads of all rows in one round trip), then the warp
+    // streams the rows out one after the other.
+    const int nw = gridDim.x * (kBlendBwdThreads / 32);
+    const int w0 = blockIdx.x * (kBlendBwdThreads / 32) + wid;
     const bool vec = (L & 3) == 0 && (l0 & 3) == 0;
-    for (int r = blockIdx.x * (kBlendThreads / 32) + wid; r < n3; r += nw) {
-        const int v = r / 3, k = r % 3;
-        float gs = g_posed[r];
-        for (int j = 0; j < J; ++j) gs += __ldg(J_regressor + (size_t)j * V + v) * s_dJ[j][k];
-        if (lane == 0) {
-            if (d_delta_vertex) d_delta_vertex[r] = gs;
-            if (d_v_shaped) d_v_shaped[r] = gs;
+    for (int rbase = w0; rbase < n3; rbase += 32 * nw) {
+        const int my = rbase + lane * nw;
+        float gs_l = 0.f;
+        if (my < n3) {
+            const int v = my / 3, k = my % 3;
+            float jr[kMaxJ];
+#pragma unroll
+            for (int j = 0; j < kMaxJ; ++j) jr[j] = j < J ? __ldg(J_regressor + (size_t)j * V + v) : 0.0f;
+            gs_l = g_posed[my];
+#pragma unroll
+            for (int j = 0; j < kMaxJ; ++j) gs_l += jr[j] * s_dJ[j < J ? j : 0][k];
+            if (d_delta_vertex) d_delta_vertex[my] = gs_l;
+            if (d_v_shaped) d_v_shaped[my] = gs_l;
         }
         if (d_delta_shapedirs) {
-            float* row = d_delta_shapedirs + (size_t)r * L;
-            if (vec) {
-                const float4* b4 = reinterpret_cast<const float4*>(betas);
-                for (int c = lane; c < (L >> 2); c += 32) {
-                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (4 * c >= l0) {
-                        const float4 b = __ldg(b4 + c);
-                        o = make_float4(b.x * gs, b.y * gs, b.z * gs, b.w * gs);
+            for (int i = 0; i < 32; ++i) {
+                const int r = rbase + i * nw;
+                if (r >= n3) break;
+                const float gs = __shfl_sync(0xffffffffu, gs_l, i);
+                float* row = d_delta_shapedirs + (size_t)r * L;
+                if (vec) {
+                    const float4* b4 = reinterpret_cast<const float4*>(betas);
+                    for (int c = lane; c < (L >> 2); c += 32) {
+                        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (4 * c >= l0) {
+                            const float4 b = __ldg(b4 + c);
+                            o = make_float4(b.x * gs, b.y * gs, b.z * gs, b.w * gs);
+                        }
+                        __stcs(reinterpret_cast<float4*>(row) + c, o);
                     }
-                    __stcs(reinterpret_cast<float4*>(row) + c, o);
+                } else {
+                    for (int c = lane; c < L; c += 32) __stcs(row + c, c >= l0 ? __ldg(betas + c) * gs : 0.0f);
                 }
-            } else {
-                for (int c = lane; c < L; c += 32) __stcs(row + c, c >= l0 ? __ldg(betas + c) * gs : 0.0f);
             }
         }
     }
@@ -516,13 +584,13 @@ int fs_flame_backward(int V, int L, int l0, int J, const int* parents_host, cons
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     FsStageTimer timer(FS_STAGE_FLAME_BWD, st);
     float* g_posed = d_dL_dv_posed ? d_dL_dv_posed : reinterpret_cast<float*>(ws + w.g_posed);
-    flame_skin_backward_kernel<<<w.nblk_skin, kSkinThreads, 0, st>>>(
+    flame_skin_backward_kernel<<<w.nblk_skin, kSkinBwdThreads, 0, st>>>(
         V, J, d_lbs_weights, reinterpret_cast<const FlameState*>(ws + w.state),
         reinterpret_cast<const float*>(ws + w.v_posed), d_dL_dverts, g_posed, reinterpret_cast<float*>(ws + w.dapart));
     // enough CTAs to stream the 4 L V 3-byte delta_shapedirs gradient at full rate, few enough that the
     // redundant prologue (partials reduce + chain backward) stays negligible
     const int grid = d_dL_ddelta_shapedirs ? 2 * fs_num_sms() : fs_num_sms() / 2 + 1;
-    fs_launch_pdl(flame_blend_backward_kernel, dim3(grid), dim3(kBlendThreads), 0, st, V, L, l0, J, P, w.nblk_skin,
+    fs_launch_pdl(flame_blend_backward_kernel, dim3(grid), dim3(kBlendBwdThreads), 0, st, V, L, l0, J, P, w.nblk_skin,
                   d_betas, d_J_regressor, reinterpret_cast<const FlameState*>(ws + w.state),
                   (const float*)g_posed, reinterpret_cast<const float*>(ws + w.dapart), d_dL_ddelta_vertex,
                   d_dL_ddelta_shapedirs, d_dL_ddelta_posedirs, d_dL_dv_shaped);
