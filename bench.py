@@ -4,9 +4,11 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl new|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
 
-Workload (config 2): 512x512, 100 000 splats riding a posed head-sized mesh (V=5002, F=10000), SH degree 0.  One
-frame = pose stage (mesh vertices -> splat position/scale/rotation/opacity, fs_pose_forward) + forward render +
-backward to xyz/scale/rot/opacity/SH (fs_backward) + pose backward to the mesh vertices and raw splat parameters.
+Workload (config 2): 512x512, 100 000 splats riding a FLAME-posed head-sized mesh (V=5002, F=10000, 400 blendshape
+coefficients, 5 joints), SH degree 0.  One frame = FLAME skinning with personalised deltas (expression/pose ->
+vertices, fs_flame_forward) + pose stage (vertices -> splat position/scale/rotation/opacity, fs_pose_forward) +
+forward render + backward to xyz/scale/rot/opacity/SH (fs_backward) + pose backward to the vertices and raw splat
+parameters + FLAME backward to delta_shapedirs / delta_posedirs / delta_vertex (fs_flame_backward).
 A "step" is one frame; frames shard one camera per GPU, so with N ranks every rank processes its own frame per step
 and the parameter gradients are all-reduced over NCCL (weak scaling).
 
@@ -20,7 +22,8 @@ roofline     dominant kernel (blend backward): algorithmic bytes (76 R + 20 W H 
 cpu_baseline the C oracle (a port of the reference's algorithm; the reference has no CPU implementation) timed on
              the host cores for a bounded sample of the same frames.
 gpu_reference (extra) the reference's own CUDA rasterizer (oracle/_ref, built by oracle/build_ref.py) driven the
-             way the reference drives it -- pose stage as plain torch ops under autograd -- on the same GPU/frames.
+             way the reference drives it -- FLAME lbs (twice) and the pose stage as plain torch ops under autograd --
+             on the same GPU/frames.
 
 --impl reference runs the CPU arm only (oracle port, all host threads), as the tier contract asks.
 """
@@ -54,19 +57,29 @@ def parse():
 
 
 def workload_config(args):
-    return {"workload": f"config2: FateAvatar-scale posed head mesh, {args.P} Gaussians, {args.res}x{args.res}, SH0, "
-                        f"pose + forward + backward per frame", "frames_in_ring": N_RING,
+    return {"workload": f"config2: FateAvatar-scale FLAME-posed head mesh, {args.P} Gaussians, {args.res}x{args.res}, SH0, "
+                        f"FLAME lbs + pose + render forward + backward (to splat parameters and FLAME deltas) per frame",
+            "frames_in_ring": N_RING,
             "l2_policy": f"ring of {N_RING} distinct frames (inputs+workspaces ~45 MB each > 126 MB L2 in total)",
             "parallelism": f"frames sharded one per GPU (dp{args.gpus}), NCCL all-reduce of Gaussian grads"}
 
 
+FLAME_KEYS = ("v_template", "shapedirs", "posedirs", "J_regressor", "lbs_weights")
+DELTA_KEYS = ("delta_vertex", "delta_shapedirs", "delta_posedirs")
+
+
 def make_frames(args, n, seed0=0):
-    """n frames of one avatar: shared splat parameters / splat sites (the model), per-frame posed vertices."""
+    """n frames of one avatar: shared splat parameters / splat sites and FLAME-shaped model (the model), per-frame
+    expression + pose coefficients (what the dataset supplies, train/dataset.py)."""
     import numpy as np
 
     from fateavatar_b200 import scenes
 
     base = scenes.pose_inputs(N=args.P, seed=seed0)
+    base.pop("verts")
+    fl = scenes.flame_inputs(seed=seed0)  # same 5002-vertex template the splat sites were sampled on
+    base.update({k: fl[k] for k in FLAME_KEYS + DELTA_KEYS})
+    base.update(parents=[int(x) for x in fl["parents"]], n_shape=fl["n_shape"], canon_verts=fl["v_template"])
     rng = np.random.default_rng(seed0 + 7)
     base["shs"] = ((rng.uniform(0, 1, (args.P, 1, 3)) - 0.5) / scenes.SH_C0).astype(np.float32)
     base["bg"] = np.ones(3, np.float32)
@@ -74,15 +87,21 @@ def make_frames(args, n, seed0=0):
     frames = []
     for i in range(n):
         f = dict(base)
-        f["verts"] = scenes.pose_inputs(N=1, seed=seed0 + 1000 + i)["verts"]  # this frame's posed mesh
+        fi = scenes.flame_inputs(seed=seed0 + 1000 + i, V=8, with_deltas=False)  # only this frame's coefficients
+        f["betas"], f["pose"] = fi["betas"], fi["pose"]
         frames.append(f)
     return frames
 
 
-def cpu_pose_and_render(f, dpix, orc, po, torch):
-    """One frame on the CPU: torch pose stage (the reference's formulation) + C oracle rasterizer, fwd+bwd."""
+def cpu_pose_and_render(f, dpix, orc, po, fo, torch):
+    """One frame on the CPU: torch FLAME lbs (twice, as model/fateavatar.py:211-222) + torch pose stage (the
+    reference's formulation) + C oracle rasterizer, forward + backward."""
     tt = lambda k: torch.from_numpy(f[k])
-    verts = tt("verts").requires_grad_(True)
+    m = {k: tt(k) for k in FLAME_KEYS}
+    m["parents"] = torch.tensor(f["parents"])
+    deltas = [tt(k).requires_grad_(True) for k in DELTA_KEYS]
+    verts, _, _ = fo.forward_with_delta_blendshape(m, tt("betas"), tt("pose"), deltas[1], deltas[2], deltas[0])
+    fo.forward_with_delta_blendshape(m, tt("betas"), tt("pose"))  # verts_orig
     leaves = [tt(k).requires_grad_(True) for k in ("scaling_raw", "rotation_raw", "offset_raw", "opacity_raw")]
     faces, fi = tt("faces"), tt("face_index")
     _, canon = po.compute_face_orientation(tt("canon_verts"), faces)
@@ -138,6 +157,7 @@ def cpu_arm(args, frames, seconds, max_frames):
     import numpy as np
     import torch
 
+    from oracle import flame_oracle as fo
     from oracle import oracle as orc
     from oracle import pose_oracle as po
 
@@ -147,11 +167,11 @@ def cpu_arm(args, frames, seconds, max_frames):
     t0 = time.perf_counter()
     n = 0
     while n < max_frames and (n < 2 or time.perf_counter() - t0 < seconds):
-        cpu_pose_and_render(frames[n % len(frames)], dpix, orc, po, torch)
+        cpu_pose_and_render(frames[n % len(frames)], dpix, orc, po, fo, torch)
         n += 1
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{n} frames of the same workload (torch pose stage + C oracle rasterizer forward+backward, "
+            "sample": f"{n} frames of the same workload (torch FLAME lbs + pose stage, C oracle rasterizer, forward+backward, "
                       f"{threads} threads) in {dt:.1f} s"}, dt / n
 
 
@@ -213,24 +233,39 @@ def main():
     a1c = torch.nn.functional.normalize(torch.cross(a0c, v2c - v0c, dim=-1), dim=-1)
     a2c = -torch.nn.functional.normalize(torch.cross(a1c, a0c, dim=-1), dim=-1)
     canon = (((v1c - v0c).norm(dim=-1) + (a2c * (v2c - v0c)).sum(-1).abs()) / 2).contiguous()  # fateavatar.py:84-85
-    verts = [tdev(f["verts"]) for f in frames]
+    fmodel = {k: tdev(f0[k]) for k in FLAME_KEYS}
+    fmodel["parents"] = f0["parents"]
+    fdelta = {k: tdev(f0[k]) for k in DELTA_KEYS}
+    betas, fpose = [tdev(f["betas"]) for f in frames], [tdev(f["pose"]) for f in frames]
+    n_shape, V, L = f0["n_shape"], f0["v_template"].shape[0], f0["shapedirs"].shape[-1]
+    NPF = (len(f0["parents"]) - 1) * 9
     rs = R.GaussianRasterizationSettings(args.res, args.res, cam["tanfovx"], cam["tanfovy"], bg, 1.0, cam["viewmatrix"],
                                          cam["projmatrix"], 0, cam["campos"], False, False)
     dpix = [torch.randn(3, args.res, args.res, device=dev) for _ in range(N_RING)]
-    # rasterizer gradients land in views of one flat scratch; parameter gradients (what DDP would all-reduce:
-    # scaling 3, rotation 4, offset 1, opacity 1, SH 3, screen-space stats 3 per splat + mesh vertices) in another
+    # rasterizer gradients land in views of one flat scratch; the PARAMETER gradients (what data-parallel training
+    # all-reduces, SURVEY 8e: scaling 3, rotation 4, offset 1, opacity 1 per splat, then delta_shapedirs,
+    # delta_posedirs, delta_vertex; SH and the screen-space densification statistic ride in a second view) land
+    # directly in views of one flat bucket, so there is no pack copy
     widths = dict(means3D=3, scales=3, rotations=4, opacity=1, sh=3, means2D=3)
     rbuf = torch.zeros(P * sum(widths.values()), device=dev)
     rv, off = {}, 0
     for k, w in widths.items():
         rv[k] = rbuf[off:off + P * w]
         off += P * w
-    V = verts[0].shape[0]
-    pbucket = torch.zeros(P * 9 + V * 3, device=dev)
-    pv = (pbucket[P * 9:].view(V, 3), pbucket[0:3 * P].view(P, 3), pbucket[3 * P:7 * P].view(P, 4),
+    o_ds, o_dp, o_dv = 9 * P, 9 * P + 3 * V * L, 9 * P + 3 * V * L + NPF * 3 * V
+    pbucket = torch.zeros(o_dv + 3 * V, device=dev)
+    d_verts = torch.empty(V, 3, device=dev)
+    pv = (d_verts, pbucket[0:3 * P].view(P, 3), pbucket[3 * P:7 * P].view(P, 4),
           pbucket[7 * P:8 * P].view(P, 1), pbucket[8 * P:9 * P].view(P, 1))
+    fgrads = [pbucket[o_dv:o_dv + 3 * V].view(V, 3), pbucket[o_ds:o_dp].view(V, 3, L), pbucket[o_dp:o_dv].view(NPF, 3 * V)]
     pose_out = [(torch.empty(P, 3, device=dev), torch.empty(P, 3, device=dev), torch.empty(P, 4, device=dev),
                  torch.empty(P, 1, device=dev)) for _ in range(N_RING)]
+    from fateavatar_b200 import flame
+
+    fl_out = [flame.flame_forward_raw(betas[k], fpose[k], fmodel["v_template"], fmodel["shapedirs"], fmodel["posedirs"],
+                                      fmodel["J_regressor"], fmodel["parents"], fmodel["lbs_weights"],
+                                      fdelta["delta_vertex"], fdelta["delta_shapedirs"], fdelta["delta_posedirs"],
+                                      l0=n_shape) for k in range(N_RING)]
 
     R.set_async(True)  # no host synchronisation inside the step; overflow is checked after the timed region
     ring = [None] * N_RING
@@ -238,18 +273,26 @@ def main():
 
     def step(i):
         k = i % N_RING
-        xyz, sc, ro, op = pose.pose_forward_raw(verts[k], faces, fidx, bary, canon, *params, shell_len=f0["shell_len"],
+        fo_ = flame.flame_forward_raw(betas[k], fpose[k], fmodel["v_template"], fmodel["shapedirs"], fmodel["posedirs"],
+                                      fmodel["J_regressor"], fmodel["parents"], fmodel["lbs_weights"],
+                                      fdelta["delta_vertex"], fdelta["delta_shapedirs"], fdelta["delta_posedirs"],
+                                      l0=n_shape, out=fl_out[k])
+        verts_k = fo_["verts"]
+        xyz, sc, ro, op = pose.pose_forward_raw(verts_k, faces, fidx, bary, canon, *params, shell_len=f0["shell_len"],
                                                 out=pose_out[k])
         color, radii, st = R.forward_raw(rs, xyz, shs, None, op, sc, ro, None)
         R.backward_raw(st, dpix[k], out=rv)
-        pose.pose_backward_raw(verts[k], faces, fidx, bary, canon, *params, rv["means3D"].view(P, 3),
+        pose.pose_backward_raw(verts_k, faces, fidx, bary, canon, *params, rv["means3D"].view(P, 3),
                                rv["scales"].view(P, 3), rv["rotations"].view(P, 4), rv["opacity"].view(P, 1),
                                shell_len=f0["shell_len"], out=pv)
+        flame.flame_backward_raw(betas[k], fmodel["J_regressor"], fmodel["parents"], fmodel["lbs_weights"],
+                                 fo_["workspace"], d_verts, (V, L), l0=n_shape, out=fgrads)
         if dist is not None:
             dist.all_reduce(pbucket)
-            dist.all_reduce(rv["sh"])
+            dist.all_reduce(rbuf[P * 10:])  # SH + screen-space statistic
         ring[k] = st  # keeps N_RING workspaces alive => consecutive steps touch different memory
-        launches[0] = st["launches"] + st.get("launches_bwd", 0) + 2 + 2 + 1  # + memset nodes + 2 pose kernels
+        # 2 memset nodes (rasterizer) + 1 (pose backward) + 2 pose + 4 FLAME kernels
+        launches[0] = st["launches"] + st.get("launches_bwd", 0) + 2 + 2 + 1 + 4
         return color
 
     def barrier():
@@ -298,7 +341,12 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    n_act = L - n_shape
     alg = {"pose_forward": P * (8 + 12 + 12 + 16 + 4 + 4 + 72) + P * 44, "pose_backward": P * (128 + 44) + P * 36 * 2,
+           # active columns of shapedirs + delta, posedirs + delta, small per-vertex arrays in; two meshes out
+           "flame_forward": 2 * 4 * 3 * V * n_act + 2 * 4 * NPF * 3 * V + 4 * V * (3 + 3 + 5 + 5) + 2 * 12 * V,
+           # dL/dverts in; dense delta_shapedirs / delta_posedirs / delta_vertex gradients out
+           "flame_backward": 12 * V + 4 * 3 * V * L + 4 * NPF * 3 * V + 12 * V,
            "blend_backward": 76 * Rn + 20 * args.res * args.res + 8 * Tn,
            "blend_forward": 40 * Rn + 20 * args.res * args.res + 8 * Tn,
            "preprocess": 52 * P + (40 + 12) * P,
@@ -324,28 +372,33 @@ def main():
         return
 
     # ---- e2e: public operator API, host buffers in, loss + image out --------------------------------------
-    # The splat parameters are model state and stay on the device; what arrives from the host every frame is the
-    # frame itself: posed mesh vertices, camera matrices and the target image.
+    # The splat parameters and the FLAME model are model state and stay on the device; what arrives from the host
+    # every frame is the frame itself (train/dataset.py): expression + pose coefficients, camera matrices and the
+    # target image.
     R.set_async(False)
     host = []
     for f in frames:
         c = f["camera"]
-        h = dict(verts=torch.from_numpy(f["verts"]), view=torch.from_numpy(c["viewmatrix"]),
-                 proj=torch.from_numpy(c["projmatrix"]), campos=torch.from_numpy(c["campos"]),
-                 target=torch.rand(3, args.res, args.res))
+        h = dict(expression=torch.from_numpy(f["betas"][n_shape:])[None], flame_pose=torch.from_numpy(f["pose"])[None],
+                 view=torch.from_numpy(c["viewmatrix"]), proj=torch.from_numpy(c["projmatrix"]),
+                 campos=torch.from_numpy(c["campos"]), target=torch.rand(3, args.res, args.res))
         host.append({k: v.contiguous().pin_memory() for k, v in h.items()})
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
     out_img = torch.empty(3, args.res, args.res).pin_memory()
     out_loss = torch.empty(1).pin_memory()
     d2h = out_img.numel() * 4 + 4
     leaves = [p_.clone().requires_grad_(True) for p_ in params] + [shs.clone().requires_grad_(True)]
+    dleaves = {k: v.clone().requires_grad_(True) for k, v in fdelta.items()}
+    zeros_shape = torch.zeros(1, n_shape, device=dev)
 
     def e2e_step(i):
         h = host[i % N_RING]
         d = {k: v.to(dev, non_blocking=True) for k, v in h.items()}
-        vts = d["verts"].requires_grad_(True)
-        for p_ in leaves:
+        for p_ in leaves + list(dleaves.values()):
             p_.grad = None
+        full_betas = torch.cat([zeros_shape, d["expression"]], dim=1)  # flame/FLAME.py:180
+        vts, _, _, vts_orig, _ = flame.flame_lbs(fmodel, full_betas, d["flame_pose"], dleaves["delta_shapedirs"],
+                                                 dleaves["delta_posedirs"], dleaves["delta_vertex"], l0=n_shape)
         xyz, sc, ro, op = pose.pose_splats(vts, faces, fidx, bary, canon, *leaves[:4], shell_len=f0["shell_len"])
         settings = R.GaussianRasterizationSettings(args.res, args.res, cam["tanfovx"], cam["tanfovy"], bg, 1.0, d["view"],
                                                    d["proj"], 0, d["campos"], False, False)
@@ -355,7 +408,7 @@ def main():
         loss = (img - d["target"]).abs().mean()
         loss.backward()
         if dist is not None:
-            for p_ in leaves:
+            for p_ in leaves + list(dleaves.values()):
                 dist.all_reduce(p_.grad)
         out_img.copy_(img.detach(), non_blocking=True)
         out_loss.copy_(loss.detach().reshape(1), non_blocking=True)
@@ -376,8 +429,8 @@ def main():
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     e2e = {"value": world * e2e_steps / (float(t_ms.item()) / 1000.0), "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-           "api": "fateavatar_b200.pose.pose_splats + GaussianRasterizer (drop-in operator API) under autograd, L1 "
-                  "loss, default synchronous mode"}
+           "api": "fateavatar_b200.flame.flame_lbs + pose.pose_splats + GaussianRasterizer (drop-in operator API) under "
+                  "autograd, L1 loss, default synchronous mode"}
 
     # ---- the reference's own CUDA rasterizer on the same GPU / frames (extra, rank 0) ----------------------
     gpu_ref = None
@@ -410,14 +463,22 @@ def main():
                             a[14], a[15], a[16], g, ctx.Rr, b_, im, False)
                         return g3, gsh, gop, gsc, gro
 
+                from oracle import flame_oracle as fo
+
                 rleaves = [p_.clone().requires_grad_(True) for p_ in params] + [shs.clone().requires_grad_(True)]
+                rdelta = {k: v.clone().requires_grad_(True) for k, v in fdelta.items()}
                 canon_col = canon.reshape(-1, 1)
+                fm_t = dict(fmodel)
+                fm_t["parents"] = torch.tensor(f0["parents"], device=dev)
 
                 def ref_step(i):
                     k = i % N_RING
-                    vts = verts[k].clone().requires_grad_(True)
-                    for p_ in rleaves:
+                    for p_ in rleaves + list(rdelta.values()):
                         p_.grad = None
+                    with torch.device(dev):  # the restated lbs creates its small constants on the default device
+                        vts, _, _ = fo.forward_with_delta_blendshape(fm_t, betas[k], fpose[k], rdelta["delta_shapedirs"],
+                                                                     rdelta["delta_posedirs"], rdelta["delta_vertex"])
+                        fo.forward_with_delta_blendshape(fm_t, betas[k], fpose[k])  # verts_orig, fateavatar.py:219-222
                     xyz, sc, ro, op = po.pose_splats(vts, faces, fidx, bary, canon_col, *rleaves[:4],
                                                      shell_len=f0["shell_len"])
                     img = RefRaster.apply(xyz, rleaves[4], op, sc, ro)
@@ -433,8 +494,8 @@ def main():
                 torch.cuda.synchronize()
                 dt = time.perf_counter() - t0
                 gpu_ref = {"value": n_ref / dt, "unit": UNIT, "ms_per_step": 1000.0 * dt / n_ref, "steps": n_ref,
-                           "what": "reference path on the same GPU and frames: pose stage as the reference's torch ops "
-                                   "under autograd + reference diff-gaussian-rasterization (sm_100 build, oracle/_ref) "
+                           "what": "reference path on the same GPU and frames: FLAME lbs (x2) and pose stage as the reference's "
+                                   "torch ops under autograd + reference diff-gaussian-rasterization (sm_100 build, oracle/_ref) "
                                    "forward+backward, 1 GPU"}
         except Exception as ex:  # never let the extra comparison break the contract line
             gpu_ref = {"error": repr(ex)}

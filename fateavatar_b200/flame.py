@@ -32,14 +32,26 @@ def _ptr(t):
 
 def flame_forward_raw(betas, pose, v_template, shapedirs, posedirs, J_regressor, parents, lbs_weights,
                       delta_vertex=None, delta_shapedirs=None, delta_posedirs=None, l0=0, want_orig=True,
-                      workspace=None):
+                      workspace=None, out=None):
     """One fs_flame_forward call on contiguous fp32 CUDA tensors (no autograd).
-    Returns dict(verts, verts_orig, pose_feature, transforms, transforms_orig, workspace)."""
+    Returns dict(verts, verts_orig, pose_feature, transforms, transforms_orig, workspace); `out` may be the dict
+    of a previous call, whose tensors are then reused instead of allocated."""
     lib = _lib.load()
     dev = v_template.device
     V, L = v_template.shape[0], shapedirs.shape[-1]
     pc, J = _parents_c(parents)
     nbytes = lib.fs_flame_workspace_bytes(V)
+    if out is not None:
+        verts, verts_orig, pf, A, A_orig, ws = (out[k] for k in ("verts", "verts_orig", "pose_feature", "transforms",
+                                                                 "transforms_orig", "workspace"))
+        with torch.cuda.device(dev):
+            rc = lib.fs_flame_forward(V, L, int(l0), J, pc, betas.data_ptr(), pose.data_ptr(), v_template.data_ptr(),
+                                      _ptr(delta_vertex), shapedirs.data_ptr(), _ptr(delta_shapedirs), posedirs.data_ptr(),
+                                      _ptr(delta_posedirs), J_regressor.data_ptr(), lbs_weights.data_ptr(),
+                                      verts.data_ptr(), _ptr(verts_orig), pf.data_ptr(), A.data_ptr(), _ptr(A_orig),
+                                      ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "fs_flame_forward")
+        return out
     ws = workspace if workspace is not None and workspace.numel() >= nbytes else torch.empty(nbytes, dtype=torch.uint8, device=dev)
     verts = torch.empty((V, 3), device=dev)
     verts_orig = torch.empty((V, 3), device=dev) if want_orig else None

@@ -202,10 +202,29 @@ def pose_inputs(N=100000, seed=0):
     )
 
 
+def _smooth_fields(rng, x, n, amp):
+    """n smooth vector fields sampled at the points x [V,3]: amp_l * sin(f_l <x, u_l> + phi_l), f in [5, 30] rad/m --
+    blendshape-like (neighbouring vertices move together), so posed triangles stay well shaped.  -> [V, 3, n]"""
+    u = rng.standard_normal((n, 3))
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    f, phi = rng.uniform(5.0, 30.0, n), rng.uniform(0, 2 * np.pi, n)
+    a = amp * rng.standard_normal((n, 3))
+    s = np.sin((x @ u.T) * f + phi)  # [V, n]
+    return s[:, None, :] * a.T[None, :, :]
+
+
+def _smooth_skin_weights(rng, x, J):
+    """Skinning weights that vary smoothly over the surface (softmax of distances to J random centres)."""
+    c = x[rng.choice(x.shape[0], J, replace=False)] * 0.7
+    d2 = ((x[:, None, :] - c[None, :, :]) ** 2).sum(-1)
+    return np.exp(-d2 / 0.08 ** 2) + 1e-3
+
+
 def flame_inputs(seed=0, V=None, n_shape=300, n_exp=100, J=5, with_deltas=True):
     """Synthetic FLAME-shaped model + one frame's coefficients (SURVEY Appendix C recipe): the licensed FLAME
     pickle cannot be shipped, so the buffers flame/FLAME.py:72-107 registers are drawn at FLAME's sizes and
-    magnitudes.  V=None uses the 5002-vertex ellipsoid template of `ellipsoid_mesh` (FLAME: 5023)."""
+    magnitudes (smooth blendshape fields of a few millimetres).  V=None uses the 5002-vertex ellipsoid template of
+    `ellipsoid_mesh` (FLAME: 5023)."""
     rng = np.random.default_rng(seed)
     if V is None:
         v_template, _ = ellipsoid_mesh()
@@ -222,17 +241,18 @@ def flame_inputs(seed=0, V=None, n_shape=300, n_exp=100, J=5, with_deltas=True):
     if J >= 3:
         pose[6] = 0.2  # jaw, cf. canonical_pose in config/fateavatar.yaml
     betas = np.concatenate([np.zeros(n_shape), 0.5 * rng.standard_normal(n_exp)])
+    posed = lambda amp: _smooth_fields(rng, v_template, NP, amp).reshape(V * 3, NP).T  # [NP, 3V]
     out = dict(
-        v_template=v_template, shapedirs=1e-3 * rng.standard_normal((V, 3, L)),
-        posedirs=1e-4 * rng.standard_normal((NP, V * 3)), J_regressor=jr / jr.sum(1, keepdims=True),
-        lbs_weights=np.exp(3.0 * rng.standard_normal((V, J))), parents=parents, betas=betas, pose=pose,
+        v_template=v_template, shapedirs=_smooth_fields(rng, v_template, L, 1e-3), posedirs=posed(1e-3),
+        J_regressor=jr / jr.sum(1, keepdims=True),
+        lbs_weights=_smooth_skin_weights(rng, v_template, J), parents=parents, betas=betas, pose=pose,
         n_shape=n_shape, n_exp=n_exp,
     )
     out["lbs_weights"] = out["lbs_weights"] / out["lbs_weights"].sum(1, keepdims=True)
     if with_deltas:
-        out["delta_shapedirs"] = 2e-4 * rng.standard_normal((V, 3, L))
-        out["delta_posedirs"] = 2e-5 * rng.standard_normal((NP, V * 3))
-        out["delta_vertex"] = 1e-3 * rng.standard_normal((V, 3))
+        out["delta_shapedirs"] = _smooth_fields(rng, v_template, L, 2e-4)
+        out["delta_posedirs"] = posed(2e-4)
+        out["delta_vertex"] = _smooth_fields(rng, v_template, 1, 1e-3)[:, :, 0]
     out = _f32(out)
     out["parents"] = parents
     return out
