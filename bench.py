@@ -61,7 +61,8 @@ def workload_config(args):
                         f"FLAME lbs + pose + render forward + backward (to splat parameters and FLAME deltas) per frame",
             "frames_in_ring": N_RING,
             "l2_policy": f"ring of {N_RING} distinct frames (inputs+workspaces ~45 MB each > 126 MB L2 in total)",
-            "parallelism": f"frames sharded one per GPU (dp{args.gpus}), NCCL all-reduce of Gaussian grads"}
+            "parallelism": f"frames sharded one per GPU (dp{args.gpus}); NCCL all-reduce of the splat gradients, all-gather "
+                           f"of the rank-1 factors of the FLAME delta gradients (expanded locally)"}
 
 
 FLAME_KEYS = ("v_template", "shapedirs", "posedirs", "J_regressor", "lbs_weights")
@@ -129,6 +130,25 @@ class ClockSampler(threading.Thread):
         self.index, self.rows, self.stop_flag = index, [], False
 
     def run(self):
+        try:  # NVML in-process: ~0.1 ms per sample, so even a short timed region is covered
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+            while not self.stop_flag:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                row = [str(self.index), str(sm), str(mx), "", hex(r)]
+                row += ["Active" if (r & bits[k]) else "Not Active" for k in ("hw_slowdown", "hw_thermal_slowdown",
+                                                                              "sw_thermal_slowdown", "sw_power_cap")]
+                self.rows.append(row)
+                time.sleep(0.002)
+            return
+        except Exception:
+            pass
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
@@ -262,6 +282,8 @@ def main():
                  torch.empty(P, 1, device=dev)) for _ in range(N_RING)]
     from fateavatar_b200 import flame
 
+    record = torch.zeros(flame.factor_record_floats(V, L, NPF), device=dev)
+    gathered = torch.empty(world, record.numel(), device=dev)
     fl_out = [flame.flame_forward_raw(betas[k], fpose[k], fmodel["v_template"], fmodel["shapedirs"], fmodel["posedirs"],
                                       fmodel["J_regressor"], fmodel["parents"], fmodel["lbs_weights"],
                                       fdelta["delta_vertex"], fdelta["delta_shapedirs"], fdelta["delta_posedirs"],
@@ -285,10 +307,20 @@ def main():
         pose.pose_backward_raw(verts_k, faces, fidx, bary, canon, *params, rv["means3D"].view(P, 3),
                                rv["scales"].view(P, 3), rv["rotations"].view(P, 4), rv["opacity"].view(P, 1),
                                shell_len=f0["shell_len"], out=pv)
-        flame.flame_backward_raw(betas[k], fmodel["J_regressor"], fmodel["parents"], fmodel["lbs_weights"],
-                                 fo_["workspace"], d_verts, (V, L), l0=n_shape, out=fgrads)
-        if dist is not None:
-            dist.all_reduce(pbucket)
+        if dist is None:
+            flame.flame_backward_raw(betas[k], fmodel["J_regressor"], fmodel["parents"], fmodel["lbs_weights"],
+                                     fo_["workspace"], d_verts, (V, L), l0=n_shape, out=fgrads)
+        else:
+            # the FLAME delta gradients are rank-1 per frame: exchange their factors (~120 KB per rank) and expand
+            # the sum locally instead of all-reducing 26 MB; splat gradients are all-reduced
+            flame.flame_backward_raw(betas[k], fmodel["J_regressor"], fmodel["parents"], fmodel["lbs_weights"],
+                                     fo_["workspace"], d_verts, (V, L), l0=n_shape, want=(False, False, False),
+                                     factor_out=(record[L + NPF:L + NPF + 3 * V].view(V, 3),
+                                                 record[L + NPF + 3 * V:L + NPF + 6 * V].view(V, 3)))
+            record[:L].copy_(betas[k])
+            record[L:L + NPF].copy_(fo_["pose_feature"])
+            flame.allgather_delta_grads(record, V, L, NPF, l0=n_shape, out=fgrads, gathered=gathered)
+            dist.all_reduce(pbucket[:9 * P])
             dist.all_reduce(rbuf[P * 10:])  # SH + screen-space statistic
         ring[k] = st  # keeps N_RING workspaces alive => consecutive steps touch different memory
         # 2 memset nodes (rasterizer) + 1 (pose backward) + 2 pose + 4 FLAME kernels

@@ -13,7 +13,8 @@ void fs_launch_preprocess(int P, int D, int M, const float* means3D, const float
                           int prefiltered, int* radii, char* ws, const fs_workspace_layout& L, cudaStream_t stream);
 void fs_launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,
                             cudaStream_t stream);
-void fs_launch_binning(int P, int W, int H, char* ws, const fs_workspace_layout& L, cudaStream_t stream);
+void fs_launch_binning(int P, int W, int H, char* ws, const fs_workspace_layout& L, fs_frame_info* host_info_dev,
+                       cudaStream_t stream);
 void fs_launch_blend_forward(int W, int H, const float* bg, float* out_color, char* ws, const fs_workspace_layout& L,
                              cudaStream_t stream);
 void fs_launch_backward(int P, int D, int M, const float* bg, int W, int H, const float* means3D, const float* shs,
@@ -215,7 +216,18 @@ int fs_forward(int P, int D, int M, const float* d_background, int width, int he
     fs_launch_preprocess(P, D, M, d_means3D, d_scales, scale_modifier, d_rotations, d_opacities, d_shs,
                          d_cov3D_precomp, d_colors_precomp, d_viewmatrix, d_projmatrix, d_cam_pos, width, height,
                          tan_fovx, tan_fovy, prefiltered, d_radii, ws, L, st);
-    fs_launch_binning(P, width, height, ws, L, st);
+    // If h_info is pinned memory the device can address, the scan kernel also stores R / overflow there directly
+    // (early notification); the full header is still copied at the end of the frame.
+    fs_frame_info* h_info_dev = nullptr;
+    if (h_info) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, h_info) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+            attr.devicePointer != nullptr)
+            h_info_dev = static_cast<fs_frame_info*>(attr.devicePointer);
+        else
+            cudaGetLastError();  // pageable memory: not an error, just no early notification
+    }
+    fs_launch_binning(P, width, height, ws, L, h_info_dev, st);
     fs_launch_blend_forward(width, height, d_background, d_out_color, ws, L, st);
     if (h_info)
         FS_CUDA_CHECK(cudaMemcpyAsync(h_info, ws + L.info, sizeof(fs_frame_info), cudaMemcpyDeviceToHost, st));

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(kScanThreads)
 tile_scan_kernel(int Tn, const uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_cursor,
                  uint2* __restrict__ ranges, uint32_t* __restrict__ big_tiles, uint32_t* __restrict__ work_order,
                  uint32_t* __restrict__ seg_base, uint2* __restrict__ seg_info, uint4* __restrict__ tile_meta,
-                 fs_frame_info* __restrict__ info, uint32_t Rcap) {
+                 fs_frame_info* __restrict__ info, volatile fs_frame_info* host_info, uint32_t Rcap) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_wmax[32];
     __shared__ uint32_t s_nbig;
@@ -97,6 +97,17 @@ tile_scan_kernel(int Tn, const uint32_t* __restrict__ tile_count, uint32_t* __re
             info->num_rendered = wi;
             info->overflow = (wi > Rcap) ? 1u : 0u;
             info->max_tile_instances = m;
+            if (host_info) {
+                // early notification: the caller's pinned header learns R / overflow as soon as they exist, long
+                // before the frame finishes, so a host that must know R (the reference's blocking read,
+                // rasterizer_impl.cu:281) can keep queueing work behind this frame instead of idling the GPU.
+                // num_rendered is written last: the host polls it.
+                host_info->overflow = (wi > Rcap) ? 1u : 0u;
+                host_info->max_tile_instances = m;
+                host_info->num_visible = info->num_visible;
+                __threadfence_system();
+                host_info->num_rendered = wi;
+            }
         }
     }
     __syncthreads();
@@ -390,7 +401,8 @@ big_tile_sort_kernel(const uint32_t* __restrict__ big_tiles, const uint2* __rest
 
 }  // namespace
 
-void fs_launch_binning(int P, int W, int H, char* ws, const fs_workspace_layout& L, cudaStream_t stream) {
+void fs_launch_binning(int P, int W, int H, char* ws, const fs_workspace_layout& L, fs_frame_info* host_info_dev,
+                       cudaStream_t stream) {
     const int gx = (W + FS_TILE - 1) / FS_TILE, gy = (H + FS_TILE - 1) / FS_TILE, Tn = gx * gy;
     const uint32_t Rcap = (uint32_t)L.instance_capacity;
     auto* info = reinterpret_cast<fs_frame_info*>(ws + L.info);
@@ -414,7 +426,7 @@ void fs_launch_binning(int P, int W, int H, char* ws, const fs_workspace_layout&
     {
         FsStageTimer t(FS_STAGE_TILE_SCAN, stream);
         fs_launch_pdl(tile_scan_kernel, dim3(1), dim3(kScanThreads), 0, stream, Tn, tile_count, tile_cursor, ranges, big,
-                      work_order, seg_base, seg_info, tile_meta, info, Rcap);
+                      work_order, seg_base, seg_info, tile_meta, info, (volatile fs_frame_info*)host_info_dev, Rcap);
     }
     {
         FsStageTimer t(FS_STAGE_SCATTER, stream);

@@ -488,6 +488,75 @@ flame_blend_backward_kernel(int V, int L, int l0, int J, Parents parents, int nb
     }
 }
 
+// ---- multi-GPU: dense delta gradients from the per-rank rank-1 factors --------------------------
+// Data-parallel training needs sum_r dL_r/d(delta_shapedirs), 24 MB per rank, but each rank's term is rank-1:
+// dL/dv_shaped_r (x) betas_r (and pose_feature_r (x) dL/dv_posed_r for delta_posedirs).  The ranks all-gather the
+// factors (~120 KB each) and every rank expands the sum locally.  Factor record per rank:
+//   [ betas L | pose_feature NP | dL/dv_shaped 3V | dL/dv_posed 3V ]
+constexpr int kMaxRanks = FS_FLAME_MAX_RANKS;
+__global__ void __launch_bounds__(kBlendBwdThreads)
+flame_expand_kernel(int N, int V, int L, int l0, int NP, const float* __restrict__ factors, size_t stride, float scale,
+                    float* __restrict__ d_delta_vertex, float* __restrict__ d_delta_shapedirs,
+                    float* __restrict__ d_delta_posedirs) {
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int n3 = 3 * V;
+    const size_t o_pf = L, o_gs = (size_t)L + NP, o_gp = (size_t)L + NP + n3;
+    if (d_delta_posedirs) {
+        const int nthreads = gridDim.x * kBlendBwdThreads;
+        for (int e = blockIdx.x * kBlendBwdThreads + t; e < n3; e += nthreads) {
+            float g[kMaxRanks];
+#pragma unroll
+            for (int r = 0; r < kMaxRanks; ++r) g[r] = r < N ? factors[r * stride + o_gp + e] * scale : 0.0f;
+            for (int i = 0; i < NP; ++i) {
+                float o = 0.f;
+#pragma unroll
+                for (int r = 0; r < kMaxRanks; ++r)
+                    if (r < N) o += __ldg(factors + r * stride + o_pf + i) * g[r];
+                __stcs(d_delta_posedirs + (size_t)i * n3 + e, o);
+            }
+        }
+    }
+    const int nw = gridDim.x * (kBlendBwdThreads / 32);
+    const bool vec = (L & 3) == 0 && (l0 & 3) == 0 && (stride & 3) == 0;
+    for (int row = blockIdx.x * (kBlendBwdThreads / 32) + wid; row < n3; row += nw) {
+        float gs[kMaxRanks], sum = 0.f;
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r) {
+            gs[r] = r < N ? factors[r * stride + o_gs + row] * scale : 0.0f;
+            sum += gs[r];
+        }
+        if (lane == 0 && d_delta_vertex) d_delta_vertex[row] = sum;
+        if (!d_delta_shapedirs) continue;
+        float* out = d_delta_shapedirs + (size_t)row * L;
+        if (vec) {
+            for (int c = lane; c < (L >> 2); c += 32) {
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (4 * c >= l0) {
+#pragma unroll
+                    for (int r = 0; r < kMaxRanks; ++r)
+                        if (r < N) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(factors + r * stride) + c);
+                            o.x += b.x * gs[r];
+                            o.y += b.y * gs[r];
+                            o.z += b.z * gs[r];
+                            o.w += b.w * gs[r];
+                        }
+                }
+                __stcs(reinterpret_cast<float4*>(out) + c, o);
+            }
+        } else {
+            for (int c = lane; c < L; c += 32) {
+                float o = 0.f;
+                if (c >= l0)
+#pragma unroll
+                    for (int r = 0; r < kMaxRanks; ++r)
+                        if (r < N) o += __ldg(factors + r * stride + c) * gs[r];
+                __stcs(out + c, o);
+            }
+        }
+    }
+}
+
 bool parents_ok(int J, const int* parents_host, Parents& P) {
     if (J < 1 || J > kMaxJ || !parents_host) return false;
     for (int j = 0; j < kMaxJ; ++j) P.p[j] = 0;
@@ -597,6 +666,36 @@ int fs_flame_backward(int V, int L, int l0, int J, const int* parents_host, cons
     fs_count_launch(2);
     if (cudaGetLastError() != cudaSuccess) {
         fs_set_error("fs_flame_backward: launch failed");
+        return FS_ERR_CUDA;
+    }
+    return FS_OK;
+}
+
+int fs_flame_expand_grads(int N, int V, int L, int l0, int NP, const float* d_factors, size_t rank_stride, float scale,
+                          float* d_dL_ddelta_vertex, float* d_dL_ddelta_shapedirs, float* d_dL_ddelta_posedirs,
+                          void* stream) {
+    if (N < 1 || N > kMaxRanks || V <= 0 || L <= 0 || l0 < 0 || l0 > L || NP < 0 ||
+        rank_stride < (size_t)L + NP + 6 * (size_t)V) {
+        fs_set_error("fs_flame_expand_grads: invalid size (N=%d, at most %d ranks; stride >= L + NP + 6V)", N, kMaxRanks);
+        return FS_ERR_INVALID_ARGUMENT;
+    }
+    if (!d_factors) {
+        fs_set_error("fs_flame_expand_grads: required pointer is NULL");
+        return FS_ERR_INVALID_ARGUMENT;
+    }
+    if (((L | l0) & 3) == 0 && (rank_stride & 3) == 0 &&
+        ((reinterpret_cast<uintptr_t>(d_factors) | reinterpret_cast<uintptr_t>(d_dL_ddelta_shapedirs)) & 15) != 0) {
+        fs_set_error("fs_flame_expand_grads: factors / dL_ddelta_shapedirs must be 16-byte aligned");
+        return FS_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FsStageTimer timer(FS_STAGE_FLAME_BWD, st);
+    flame_expand_kernel<<<2 * fs_num_sms(), kBlendBwdThreads, 0, st>>>(N, V, L, l0, NP, d_factors, rank_stride, scale,
+                                                                      d_dL_ddelta_vertex, d_dL_ddelta_shapedirs,
+                                                                      d_dL_ddelta_posedirs);
+    fs_count_launch(1);
+    if (cudaGetLastError() != cudaSuccess) {
+        fs_set_error("fs_flame_expand_grads: launch failed");
         return FS_ERR_CUDA;
     }
     return FS_OK;

@@ -17,9 +17,11 @@ What differs underneath (see include/fatesplat.h): one caller-owned workspace in
 byte tensors, launches on torch's *current* stream (the reference uses the legacy default stream), and the
 instance count R comes back through pinned memory.  Two modes:
 
-  FATESPLAT_ASYNC=0 (default)  wait for R after the forward like the reference's blocking cudaMemcpy
-                               (rasterizer_impl.cu:281); if the workspace was too small the frame is re-run
-                               with a larger one, so results never depend on the capacity guess.
+  FATESPLAT_ASYNC=0 (default)  wait for R like the reference's blocking cudaMemcpy (rasterizer_impl.cu:281) -- but
+                               only until the scan kernel has stored it into the pinned header, i.e. ~40 us into
+                               the frame, so the host keeps queueing work while the frame renders; if the
+                               workspace was too small the frame is re-run with a larger one, so results never
+                               depend on the capacity guess.
   FATESPLAT_ASYNC=1            no host synchronisation at all; R is checked lazily (next call / backward)
                                and an overflow raises FateSplatError instead of returning a truncated frame.
 """
@@ -106,6 +108,22 @@ def _drain_pending(ent, dev, block=False):
     ent["pending"] = keep
 
 
+_POISON = 0xFFFFFFFF
+
+
+def _wait_num_rendered(info, stream):
+    """Synchronous mode: block until this frame's instance count is known, like the reference's blocking read of
+    num_rendered (rasterizer_impl.cu:281) -- but only until the scan kernel has stored it into the pinned header
+    (fs_forward's early notification), not until the frame has finished, so the host keeps the stream fed."""
+    spins = 0
+    while info.num_rendered == _POISON:
+        spins += 1
+        if (spins & 255) == 0 and stream.query():  # nothing left on the stream: the header must have arrived
+            if info.num_rendered == _POISON:
+                raise FateSplatError("fs_forward finished without reporting num_rendered (pinned header not written)")
+    return info
+
+
 def _ptr(t):
     return None if t is None or t.numel() == 0 else t.data_ptr()
 
@@ -176,6 +194,8 @@ def forward_raw(raster_settings, means3D, sh, colors_precomp, opacities, scales,
                 if _ASYNC and any(p[0] == slot for p in ent["pending"]):
                     _drain_pending(ent, di, block=True)
                 h_info = ent["buf"].data_ptr() + slot * _INFO_BYTES
+                info = _slot_info(ent, slot)
+                info.num_rendered = _POISON
                 rc = lib.fs_forward(P, D, M, _ptr(bg), W, H, _ptr(m3), _ptr(sh_c), _ptr(cp_c), _ptr(op_c),
                                     _ptr(sc_c), float(rs.scale_modifier), _ptr(ro_c), _ptr(c3_c), _ptr(view),
                                     _ptr(proj), _ptr(campos), float(rs.tanfovx), float(rs.tanfovy),
@@ -189,8 +209,7 @@ def forward_raw(raster_settings, means3D, sh, colors_precomp, opacities, scales,
                     ent["pending"].append((slot, ev, key))
                     num_rendered = -1
                     break
-                stream.synchronize()
-                info = _slot_info(ent, slot)
+                _wait_num_rendered(info, stream)
                 num_rendered = int(info.num_rendered)
                 _capacity_hint[key] = max(num_rendered, int(_capacity_hint.get(key, 0) * 0.9))
                 _tile_hint[key] = max(int(info.max_tile_instances), int(_tile_hint.get(key, 0) * 0.9))

@@ -195,6 +195,28 @@ int fs_flame_backward(int V, int L, int l0, int J, const int* parents_host, cons
                       float* d_dL_dv_posed, void* stream);
 
 /*
+ * Data-parallel exchange of the FLAME delta gradients in factored form.  Each rank's
+ * dL/d(delta_shapedirs) is the rank-1 product dL_dv_shaped (x) betas (24 MB dense), dL/d(delta_posedirs) is
+ * pose_feature (x) dL_dv_posed and dL/d(delta_vertex) is dL_dv_shaped, so ranks all-gather one small record each
+ *     [ betas L | pose_feature NP | dL_dv_shaped 3V | dL_dv_posed 3V ]        (floats; ~120 KB at FLAME sizes)
+ * and expand the SUM over ranks locally: out = scale * sum_r (record_r's outer products).  d_factors holds N such
+ * records `rank_stride` floats apart (the all-gather output).  Any output pointer may be NULL.  N <= 8.
+ */
+#define FS_FLAME_MAX_RANKS 8
+int fs_flame_expand_grads(int N, int V, int L, int l0, int NP, const float* d_factors, size_t rank_stride, float scale,
+                          float* d_dL_ddelta_vertex, float* d_dL_ddelta_shapedirs, float* d_dL_ddelta_posedirs,
+                          void* stream);
+
+/*
+ * Densification statistics (model/fateavatar.py:734-737, gaussian_model.py:418-420), in place:
+ *   xyz_gradient_accum[i] += hypot(viewspace_grad[i,0], viewspace_grad[i,1]);  denom[i] += 1   where update_filter[i]
+ * viewspace_grad [P,3] is the .grad of the dummy screen-space tensor (fs_backward's dL_dmeans2D), update_filter [P]
+ * is torch.bool / uint8 (radii > 0), xyz_gradient_accum and denom are [P,1] float.
+ */
+int fs_densify_stats(int P, const float* d_viewspace_grad, const uint8_t* d_update_filter,
+                     float* d_xyz_gradient_accum, float* d_denom, void* stream);
+
+/*
  * Optional per-stage device timing for bench.py's roofline figures.  While enabled, every stage launch is
  * bracketed by CUDA events on the launching stream; fs_profile_read waits for them and returns, per stage id
  * (0 preprocess, 1 tile_scan, 2 scatter, 3 tile_sort, 4 big_tile_sort, 5 blend_forward, 6 blend_backward,

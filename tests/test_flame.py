@@ -201,3 +201,41 @@ def test_attach_rebinds_reference_flame_module_methods(cuda_device):
         mod.forward_with_delta_blendshape(expr.clone().requires_grad_(True), pose, leaves["delta_shapedirs"], leaves["delta_posedirs"],
                                           leaves["delta_vertex"])
     assert lc0 >= 2
+
+
+@pytest.mark.gpu
+def test_expand_factors_kernel_and_single_rank_identity(cuda_device):
+    """fs_flame_expand_grads: (a) N = 3 random records vs the torch statement; (b) with N = 1 and this rank's own
+    factors it reproduces the dense gradients fs_flame_backward writes (the rank-1 structure is exact)."""
+    from fateavatar_b200 import flame
+
+    V, L, NP = 333, 400, 36
+    g = torch.Generator().manual_seed(1)
+    rec = flame.factor_record_floats(V, L, NP)
+    gathered = torch.randn(3, rec, generator=g).to(cuda_device)
+    gathered[:, :300] = 0.0
+    got = flame.expand_factors(gathered, V, L, NP, l0=300, scale=0.5)
+    want = flame.expand_factors_reference(gathered, V, L, NP, scale=0.5)
+    for a, b in zip(got, want):
+        assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
+    # scalar path: sizes that are not multiples of 4
+    gathered = torch.randn(2, flame.factor_record_floats(50, 18, 18), generator=g).to(cuda_device)
+    got = flame.expand_factors(gathered, 50, 18, 18, l0=0)
+    want = flame.expand_factors_reference(gathered, 50, 18, 18)
+    for a, b in zip(got, want):
+        assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
+
+    f = scenes.flame_inputs(seed=11, V=200)
+    m = _model(f, torch.float32, cuda_device)
+    m["parents"] = [int(x) for x in f["parents"]]
+    t = lambda k: torch.from_numpy(f[k]).to(cuda_device)
+    r = flame.flame_forward_raw(t("betas"), t("pose"), m["v_template"], m["shapedirs"], m["posedirs"], m["J_regressor"],
+                                m["parents"], m["lbs_weights"], t("delta_vertex"), t("delta_shapedirs"), t("delta_posedirs"),
+                                l0=300)
+    up = torch.randn(200, 3, generator=g).to(cuda_device)
+    dv, ds, dp, gs, gp = flame.flame_backward_raw(t("betas"), m["J_regressor"], m["parents"], m["lbs_weights"], r["workspace"],
+                                                  up, (200, 400), l0=300, factors=True)
+    record = torch.zeros(1, flame.factor_record_floats(200, 400, 36), device=cuda_device)
+    flame.pack_factors(record[0], t("betas"), r["pose_feature"], gs, gp)
+    ev, es, ep = flame.expand_factors(record, 200, 400, 36, l0=300)
+    assert torch.equal(ev, dv) and torch.equal(es, ds) and torch.equal(ep, dp)

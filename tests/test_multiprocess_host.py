@@ -68,3 +68,70 @@ def test_frame_sharded_gradient_bucket_world2():
             want[off:off + P * w] += g[KEYS[k]].reshape(-1)
             off += P * w
     assert np.allclose(got, want, rtol=1e-6, atol=1e-7)
+
+
+# ---- factored exchange of the FLAME delta gradients ------------------------------------------------
+def flame_rank_grads(rank, V):
+    """Dense delta gradients of one rank's frame from the oracle's float64 autograd, and their rank-1 factors."""
+    from oracle import flame_oracle as fo
+
+    f = scenes.flame_inputs(seed=3, V=V, n_shape=8, n_exp=12)           # shared model
+    fr = scenes.flame_inputs(seed=50 + rank, V=V, n_shape=8, n_exp=12)  # this rank's coefficients
+    t = lambda a: torch.from_numpy(a).double()
+    m = {k: t(f[k]) for k in ("v_template", "shapedirs", "posedirs", "J_regressor", "lbs_weights")}
+    m["parents"] = torch.from_numpy(f["parents"])
+    leaves = {k: t(f[k]).requires_grad_(True) for k in ("delta_vertex", "delta_shapedirs", "delta_posedirs")}
+    betas, pose = t(fr["betas"]), t(fr["pose"])
+    verts, pf, _ = fo.forward_with_delta_blendshape(m, betas, pose, leaves["delta_shapedirs"], leaves["delta_posedirs"],
+                                                    leaves["delta_vertex"])
+    g = torch.from_numpy(np.random.default_rng(rank).standard_normal((V, 3)))
+    (verts * g).sum().backward()
+    dense = {k: v.grad for k, v in leaves.items()}
+    i = int(pf.abs().argmax())
+    factors = dict(betas=betas, pose_feature=pf.detach(), dL_dv_shaped=dense["delta_vertex"],
+                   dL_dv_posed=dense["delta_posedirs"][i] / pf[i].detach())
+    return dense, factors
+
+
+def _flame_worker(rank, world, port, V, out):
+    from fateavatar_b200 import flame
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    _, fac = flame_rank_grads(rank, V)
+    L, NP = fac["betas"].numel(), fac["pose_feature"].numel()
+    rec = torch.zeros(flame.factor_record_floats(V, L, NP), dtype=torch.float64)
+    flame.pack_factors(rec, fac["betas"], fac["pose_feature"], fac["dL_dv_shaped"], fac["dL_dv_posed"])
+    gathered = torch.empty(world, rec.numel(), dtype=torch.float64)
+    dist.all_gather_into_tensor(gathered.view(-1), rec)
+    dv, ds, dp = flame.expand_factors_reference(gathered, V, L, NP)
+    if rank == 0:
+        out.put((dv.numpy(), ds.numpy(), dp.numpy(), rec.numel()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_factored_flame_delta_gradient_exchange_world2():
+    """All-gathering the per-rank factor records and expanding locally equals all-reducing the dense gradients."""
+    V, world = 40, 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_flame_worker, args=(r, world, port, V, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    dv, ds, dp, nrec = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = None
+    for r in range(world):
+        dense, _ = flame_rank_grads(r, V)
+        want = dense if want is None else {k: want[k] + dense[k] for k in want}
+    assert np.allclose(dv, want["delta_vertex"].numpy(), rtol=1e-10, atol=1e-12)
+    assert np.allclose(ds, want["delta_shapedirs"].numpy(), rtol=1e-10, atol=1e-12)
+    assert np.allclose(dp, want["delta_posedirs"].numpy(), rtol=1e-9, atol=1e-12)
+    assert nrec * 8 < 0.05 * sum(v.numel() for v in want.values()) * 8  # wire record is a few % of the dense gradients

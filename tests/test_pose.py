@@ -102,3 +102,30 @@ def test_pose_kernel_vs_oracle(N, cuda_device):
         w = np.asarray(want, np.float64)
         err = np.abs(got.cpu().numpy().astype(np.float64).reshape(w.shape) - w).max()
         assert err <= 2e-4 * max(np.abs(w).max(), 1e-12), (name, err, np.abs(w).max())
+
+
+@pytest.mark.gpu
+def test_densification_stats_kernel_matches_reference_expression(cuda_device):
+    """S1: model/fateavatar.py:734-737 evaluated with torch ops vs fs_densify_stats, in place, over two frames."""
+    import types
+
+    from fateavatar_b200 import densify
+
+    g = torch.Generator().manual_seed(0)
+    P = 10007
+    accum0, denom0 = torch.rand(P, 1, generator=g), torch.randint(0, 5, (P, 1), generator=g).float()
+    model = types.SimpleNamespace(xyz_gradient_accum=accum0.clone().to(cuda_device), denom=denom0.clone().to(cuda_device),
+                                  _add_densification_stats=None)
+    densify.attach(model)
+    ref_a, ref_d = accum0.clone(), denom0.clone()
+    for _ in range(2):
+        grad = torch.randn(P, 3, generator=g)
+        filt = torch.rand(P, generator=g) < 0.6
+        vp = types.SimpleNamespace(grad=grad.to(cuda_device))
+        model._add_densification_stats(vp, filt.to(cuda_device))
+        ref_a[filt] += torch.norm(grad[filt, :2], dim=-1, keepdim=True)
+        ref_d[filt] += 1
+    assert torch.equal(model.denom.cpu(), ref_d)
+    assert float((model.xyz_gradient_accum.cpu() - ref_a).abs().max()) <= 5e-7  # 2-term norm: last-bit rounding only
+    with pytest.raises(Exception):
+        densify.densify_stats_raw(ref_a, ref_d, grad, filt)  # CPU tensors: no CPU path
