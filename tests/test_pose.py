@@ -126,6 +126,7 @@ def test_densification_stats_kernel_matches_reference_expression(cuda_device):
         ref_a[filt] += torch.norm(grad[filt, :2], dim=-1, keepdim=True)
         ref_d[filt] += 1
     assert torch.equal(model.denom.cpu(), ref_d)
-    assert float((model.xyz_gradient_accum.cpu() - ref_a).abs().max()) <= 5e-7  # 2-term norm: last-bit rounding only
+    # 2-term norm and one add per frame: last-bit rounding only (values reach ~10, ulp ~1e-6)
+    assert float(((model.xyz_gradient_accum.cpu() - ref_a).abs() / ref_a.abs().clamp(min=1.0)).max()) <= 3e-7
     with pytest.raises(Exception):
         densify.densify_stats_raw(ref_a, ref_d, grad, filt)  # CPU tensors: no CPU path
