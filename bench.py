@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--res", type=int, default=512)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--quick", action="store_true", help="device-resident arm only (used under ncu)")
+    ap.add_argument("--no-collective", action="store_true", help="developer probe: skip the gradient exchange at N > 1")
     return ap.parse_args()
 
 
@@ -61,8 +62,8 @@ def workload_config(args):
                         f"FLAME lbs + pose + render forward + backward (to splat parameters and FLAME deltas) per frame",
             "frames_in_ring": N_RING,
             "l2_policy": f"ring of {N_RING} distinct frames (inputs+workspaces ~45 MB each > 126 MB L2 in total)",
-            "parallelism": f"frames sharded one per GPU (dp{args.gpus}); NCCL all-reduce of the splat gradients, all-gather "
-                           f"of the rank-1 factors of the FLAME delta gradients (expanded locally)"}
+            "parallelism": f"frames sharded one per GPU (dp{args.gpus}); one NCCL all-reduce per step over the splat "
+                           f"gradients + the rank-1 factors of the FLAME delta gradients (expanded locally)"}
 
 
 FLAME_KEYS = ("v_template", "shapedirs", "posedirs", "J_regressor", "lbs_weights")
@@ -181,7 +182,8 @@ def cpu_arm(args, frames, seconds, max_frames):
     from oracle import oracle as orc
     from oracle import pose_oracle as po
 
-    threads = orc.num_threads()
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    orc.set_num_threads(threads)  # explicit: torchrun exports OMP_NUM_THREADS=1
     torch.set_num_threads(threads)
     dpix = np.random.default_rng(0).standard_normal((3, args.res, args.res)).astype(np.float32)
     t0 = time.perf_counter()
@@ -197,6 +199,11 @@ def cpu_arm(args, frames, seconds, max_frames):
 
 def main():
     args = parse()
+    # stdout must carry exactly one JSON line: keep the real stdout for it and send everything else that writes to
+    # fd 1 (NCCL's version banner, library chatter) to stderr
+    global REAL_STDOUT
+    REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -205,6 +212,7 @@ def main():
         # the reference has no CPU implementation; its algorithm restated in C (oracle/) is the CPU arm
         if rank != 0:
             return
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())  # torchrun pins it to 1; this arm uses every host core
         frames = make_frames(args, 2)
         steps = max(1, min(args.steps, 40))
         for _ in range(min(args.warmup, 2)):
@@ -217,7 +225,7 @@ def main():
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "note": "reference = zjwfufu/FateAvatar's rasterizer algorithm (CUDA-only upstream) restated in C "
                         "(oracle/splat_oracle.c), run on the host cores; rank 0 only"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=REAL_STDOUT, flush=True)
         return
 
     import numpy as np
@@ -262,28 +270,33 @@ def main():
     rs = R.GaussianRasterizationSettings(args.res, args.res, cam["tanfovx"], cam["tanfovy"], bg, 1.0, cam["viewmatrix"],
                                          cam["projmatrix"], 0, cam["campos"], False, False)
     dpix = [torch.randn(3, args.res, args.res, device=dev) for _ in range(N_RING)]
-    # rasterizer gradients land in views of one flat scratch; the PARAMETER gradients (what data-parallel training
-    # all-reduces, SURVEY 8e: scaling 3, rotation 4, offset 1, opacity 1 per splat, then delta_shapedirs,
-    # delta_posedirs, delta_vertex; SH and the screen-space densification statistic ride in a second view) land
-    # directly in views of one flat bucket, so there is no pack copy
-    widths = dict(means3D=3, scales=3, rotations=4, opacity=1, sh=3, means2D=3)
-    rbuf = torch.zeros(P * sum(widths.values()), device=dev)
-    rv, off = {}, 0
-    for k, w in widths.items():
-        rv[k] = rbuf[off:off + P * w]
-        off += P * w
-    o_ds, o_dp, o_dv = 9 * P, 9 * P + 3 * V * L, 9 * P + 3 * V * L + NPF * 3 * V
-    pbucket = torch.zeros(o_dv + 3 * V, device=dev)
-    d_verts = torch.empty(V, 3, device=dev)
-    pv = (d_verts, pbucket[0:3 * P].view(P, 3), pbucket[3 * P:7 * P].view(P, 4),
-          pbucket[7 * P:8 * P].view(P, 1), pbucket[8 * P:9 * P].view(P, 1))
-    fgrads = [pbucket[o_dv:o_dv + 3 * V].view(V, 3), pbucket[o_ds:o_dp].view(V, 3, L), pbucket[o_dp:o_dv].view(NPF, 3 * V)]
-    pose_out = [(torch.empty(P, 3, device=dev), torch.empty(P, 3, device=dev), torch.empty(P, 4, device=dev),
-                 torch.empty(P, 1, device=dev)) for _ in range(N_RING)]
+    # Gradient memory.  What data-parallel training exchanges lives in ONE flat bucket, written in
+    # place by the kernels (no pack copy) and reduced by ONE collective per step:
+    #   [ splat parameter grads: scaling 3, rotation 4, offset 1, opacity 1 | SH 3 | screen-space statistic 3 ] x P
+    #   [ world x factor record of the FLAME delta gradients ]   (each rank fills its own slot, the others are zero,
+    #     so the sum all-reduce doubles as the all-gather of the rank-1 factors)
+    # Intermediate gradients (dL/dxyz, dL/dscale, ... of the rasterizer, dL/dverts) stay in scratch tensors.
     from fateavatar_b200 import flame
 
-    record = torch.zeros(flame.factor_record_floats(V, L, NPF), device=dev)
-    gathered = torch.empty(world, record.numel(), device=dev)
+    rec_n = flame.factor_record_floats(V, L, NPF)
+    bucket = torch.zeros(15 * P + world * rec_n, device=dev)
+    scratch = torch.zeros(11 * P, device=dev)
+    # bucket = [A: SH 3P, screen-space statistic 3P | B: scaling 3P, rotation 4P, offset P, opacity P | C: factors]
+    # A is complete after the rasterizer backward, B after the pose backward, C after the FLAME backward: each part
+    # is all-reduced asynchronously as soon as it exists, so A and B travel while the rest of the backward runs
+    # (what DDP does with its buckets) and only the small factor exchange is exposed.
+    rv = dict(means3D=scratch[0:3 * P], scales=scratch[3 * P:6 * P], rotations=scratch[6 * P:10 * P],
+              opacity=scratch[10 * P:11 * P], sh=bucket[0:3 * P], means2D=bucket[3 * P:6 * P])
+    d_verts = torch.empty(V, 3, device=dev)
+    pv = (d_verts, bucket[6 * P:9 * P].view(P, 3), bucket[9 * P:13 * P].view(P, 4),
+          bucket[13 * P:14 * P].view(P, 1), bucket[14 * P:15 * P].view(P, 1))
+    part_a, part_b, part_c = bucket[:6 * P], bucket[6 * P:15 * P], bucket[15 * P:]
+    fgrads = [torch.empty(V, 3, device=dev), torch.empty(V, 3, L, device=dev), torch.empty(NPF, 3 * V, device=dev)]
+    gathered = bucket[15 * P:].view(world, rec_n)
+    record = gathered[rank]
+    others = [gathered[r] for r in range(world) if r != rank]
+    pose_out = [(torch.empty(P, 3, device=dev), torch.empty(P, 3, device=dev), torch.empty(P, 4, device=dev),
+                 torch.empty(P, 1, device=dev)) for _ in range(N_RING)]
     fl_out = [flame.flame_forward_raw(betas[k], fpose[k], fmodel["v_template"], fmodel["shapedirs"], fmodel["posedirs"],
                                       fmodel["J_regressor"], fmodel["parents"], fmodel["lbs_weights"],
                                       fdelta["delta_vertex"], fdelta["delta_shapedirs"], fdelta["delta_posedirs"],
@@ -292,6 +305,8 @@ def main():
     R.set_async(True)  # no host synchronisation inside the step; overflow is checked after the timed region
     ring = [None] * N_RING
     launches = [0]
+
+    overlap = os.environ.get("FATESPLAT_BENCH_EXCHANGE", "single") == "overlap"
 
     def step(i):
         k = i % N_RING
@@ -304,24 +319,32 @@ def main():
                                                 out=pose_out[k])
         color, radii, st = R.forward_raw(rs, xyz, shs, None, op, sc, ro, None)
         R.backward_raw(st, dpix[k], out=rv)
+        exchange = dist is not None and not args.no_collective
+        wa = dist.all_reduce(part_a, async_op=True) if exchange and overlap else None
         pose.pose_backward_raw(verts_k, faces, fidx, bary, canon, *params, rv["means3D"].view(P, 3),
                                rv["scales"].view(P, 3), rv["rotations"].view(P, 4), rv["opacity"].view(P, 1),
                                shell_len=f0["shell_len"], out=pv)
-        if dist is None:
+        if not exchange:
             flame.flame_backward_raw(betas[k], fmodel["J_regressor"], fmodel["parents"], fmodel["lbs_weights"],
                                      fo_["workspace"], d_verts, (V, L), l0=n_shape, out=fgrads)
         else:
-            # the FLAME delta gradients are rank-1 per frame: exchange their factors (~120 KB per rank) and expand
-            # the sum locally instead of all-reducing 26 MB; splat gradients are all-reduced
+            wb = dist.all_reduce(part_b, async_op=True) if overlap else None
+            # the FLAME delta gradients are rank-1 per frame: exchange their factors (~120 KB per rank; every rank
+            # fills its own slot of part C, the others are zero, so the sum all-reduce is the all-gather) and expand
+            # the sum locally instead of all-reducing 26 MB
+            for o_ in others:
+                o_.zero_()
+            record[:L].copy_(betas[k])
+            record[L:L + NPF].copy_(fo_["pose_feature"])
             flame.flame_backward_raw(betas[k], fmodel["J_regressor"], fmodel["parents"], fmodel["lbs_weights"],
                                      fo_["workspace"], d_verts, (V, L), l0=n_shape, want=(False, False, False),
                                      factor_out=(record[L + NPF:L + NPF + 3 * V].view(V, 3),
                                                  record[L + NPF + 3 * V:L + NPF + 6 * V].view(V, 3)))
-            record[:L].copy_(betas[k])
-            record[L:L + NPF].copy_(fo_["pose_feature"])
-            flame.allgather_delta_grads(record, V, L, NPF, l0=n_shape, out=fgrads, gathered=gathered)
-            dist.all_reduce(pbucket[:9 * P])
-            dist.all_reduce(rbuf[P * 10:])  # SH + screen-space statistic
+            dist.all_reduce(part_c if overlap else bucket)
+            flame.expand_factors(gathered, V, L, NPF, l0=n_shape, out=fgrads)
+            if overlap:
+                wa.wait()
+                wb.wait()
         ring[k] = st  # keeps N_RING workspaces alive => consecutive steps touch different memory
         # 2 memset nodes (rasterizer) + 1 (pose backward) + 2 pose + 4 FLAME kernels
         launches[0] = st["launches"] + st.get("launches_bwd", 0) + 2 + 2 + 1 + 4
@@ -400,7 +423,7 @@ def main():
     if args.quick:
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                              "ms_per_step": ms_per_step, "kernels": kernels, "quick": True}), flush=True)
+                              "ms_per_step": ms_per_step, "kernels": kernels, "quick": True}), file=REAL_STDOUT, flush=True)
         return
 
     # ---- e2e: public operator API, host buffers in, loss + image out --------------------------------------
@@ -544,7 +567,7 @@ def main():
                 "gpu_launches": launches[0] * args.steps, "gpu_launches_per_step": launches[0], "roofline": roofline,
                 "kernels": kernels, "cpu_baseline": cb, "gpu_reference": gpu_ref,
                 "speedup_vs_gpu_reference": (value / world / gpu_ref["value"]) if gpu_ref and "value" in gpu_ref else None}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=REAL_STDOUT, flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
