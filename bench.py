@@ -13,9 +13,11 @@ A "step" is one frame; frames shard one camera per GPU, so with N ranks every ra
 and the parameter gradients are all-reduced over NCCL (weak scaling).
 
 value        frames/s of forward+backward through the C ABI with all inputs resident in HBM (no host sync).
-e2e          the same step through the public operator API (fateavatar_b200.render.render + autograd) with HOST
-             inputs: pinned H2D of the frame's Gaussian attributes, camera and target image, loss, backward,
-             D2H of loss + rendered image, all inside the timed region.
+e2e          the same frame through the public operator API under autograd (flame.flame_lbs + pose.pose_splats +
+             GaussianRasterizer, L1 loss) with HOST inputs: pinned H2D of the frame's expression/pose coefficients,
+             camera and target image, backward, D2H of the loss, all inside the timed region.  Headline = the frame
+             recorded once into a CUDA graph (fateavatar_b200.graph.CapturedStep) and replayed; `eager_value` = the
+             same frame with every operator call issued from Python.
 roofline     dominant kernel (blend backward): algorithmic bytes (76 R + 20 W H + 8 Tn) over its
              mean launch time measured with CUDA events on the launching stream (fs_profile_*), against the
              measured HBM copy bandwidth in MEASURED_PEAKS.json.
@@ -439,18 +441,14 @@ def main():
                  campos=torch.from_numpy(c["campos"]), target=torch.rand(3, args.res, args.res))
         host.append({k: v.contiguous().pin_memory() for k, v in h.items()})
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
-    out_img = torch.empty(3, args.res, args.res).pin_memory()
     out_loss = torch.empty(1).pin_memory()
-    d2h = out_img.numel() * 4 + 4
+    d2h = 4
     leaves = [p_.clone().requires_grad_(True) for p_ in params] + [shs.clone().requires_grad_(True)]
     dleaves = {k: v.clone().requires_grad_(True) for k, v in fdelta.items()}
     zeros_shape = torch.zeros(1, n_shape, device=dev)
 
-    def e2e_step(i):
-        h = host[i % N_RING]
-        d = {k: v.to(dev, non_blocking=True) for k, v in h.items()}
-        for p_ in leaves + list(dleaves.values()):
-            p_.grad = None
+    def frame(d):
+        """One frame through the public operator API under autograd; `d` holds this frame's inputs on the device."""
         full_betas = torch.cat([zeros_shape, d["expression"]], dim=1)  # flame/FLAME.py:180
         vts, _, _, vts_orig, _ = flame.flame_lbs(fmodel, full_betas, d["flame_pose"], dleaves["delta_shapedirs"],
                                                  dleaves["delta_posedirs"], dleaves["delta_vertex"], l0=n_shape)
@@ -462,30 +460,63 @@ def main():
                                                     rotations=ro)
         loss = (img - d["target"]).abs().mean()
         loss.backward()
+        return {"loss": loss.detach().reshape(1)}  # what a training step reads back (train/trainer.py: loss.item())
+
+    all_leaves = leaves + list(dleaves.values())
+
+    def eager_step(i):  # every operator call issued from Python, default synchronous mode
+        h = host[i % N_RING]
+        d = {k: v.to(dev, non_blocking=True) for k, v in h.items()}
+        for p_ in all_leaves:
+            p_.grad = None
+        out = frame(d)
         if dist is not None:
-            for p_ in leaves + list(dleaves.values()):
+            for p_ in all_leaves:
                 dist.all_reduce(p_.grad)
-        out_img.copy_(img.detach(), non_blocking=True)
-        out_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+        out_loss.copy_(out["loss"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(out_loss[0])
 
-    e2e_steps = max(10, min(args.steps, 100))
-    for i in range(5):
-        e2e_step(i)
-    barrier()
-    e0.record()
-    for i in range(e2e_steps):
-        e2e_step(i)
-    e1.record()
-    barrier()
-    t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if dist is not None:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    e2e = {"value": world * e2e_steps / (float(t_ms.item()) / 1000.0), "unit": UNIT, "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-           "api": "fateavatar_b200.flame.flame_lbs + pose.pose_splats + GaussianRasterizer (drop-in operator API) under "
-                  "autograd, L1 loss, default synchronous mode"}
+    def time_e2e(fn, n):
+        for i in range(5):
+            fn(i)
+        barrier()
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return world * n / (float(t.item()) / 1000.0)
+
+    e2e_steps = max(10, min(args.steps, 200))
+    eager_fps = time_e2e(eager_step, e2e_steps)
+
+    # the same frame recorded once into a CUDA graph (fateavatar_b200.graph.CapturedStep) and replayed: per step the
+    # host issues the H2D copies of this frame's pinned inputs, ONE graph launch (FLAME, pose, render, loss, backward,
+    # D2H of the loss into pinned memory) and a stream synchronise before it reads the loss
+    from fateavatar_b200 import graph as fgraph
+
+    cap = fgraph.CapturedStep(frame, {k: v.to(dev) for k, v in host[0].items()}, params=all_leaves)
+
+    def graph_step(i):
+        out = cap(host[i % N_RING])
+        if dist is not None:
+            for g_ in cap.grads:
+                dist.all_reduce(g_)
+        cap.wait()
+        return float(out["loss"][0])
+
+    graph_fps = time_e2e(graph_step, e2e_steps)
+    R.set_async(False)
+    e2e = {"value": graph_fps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+           "api": "fateavatar_b200.graph.CapturedStep replaying one frame of flame.flame_lbs + pose.pose_splats + "
+                  "GaussianRasterizer (drop-in operator API) under autograd with an L1 loss; host inputs (expression, pose, "
+                  "camera, target image) copied in and the loss copied out through pinned memory every step",
+           "eager_value": eager_fps,
+           "eager_api": "the same frame with every operator call issued from Python (default synchronous mode)"}
 
     # ---- the reference's own CUDA rasterizer on the same GPU / frames (extra, rank 0) ----------------------
     gpu_ref = None

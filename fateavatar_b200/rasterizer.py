@@ -59,6 +59,14 @@ _tile_hint = {}       # (device index, W, H) -> heaviest tile seen recently (fs_
 _pinned = {}          # device index -> (pinned uint8 tensor viewed as FsFrameInfo slots, next slot, events)
 _N_SLOTS = 64
 _INFO_BYTES = C.sizeof(FsFrameInfo)
+capture_headers = []  # (pinned header, hint key, capacity) of every forward recorded under CUDA-graph capture
+_capture_header_pool = []
+
+
+def reserve_capture_headers(n=4):
+    """Pre-allocate pinned frame headers for forwards that will be recorded under CUDA-graph capture."""
+    while len(_capture_header_pool) < n:
+        _capture_header_pool.append(torch.zeros(_INFO_BYTES, dtype=torch.uint8).pin_memory())
 
 
 def set_async(flag: bool):
@@ -182,11 +190,33 @@ def forward_raw(raster_settings, means3D, sh, colors_precomp, opacities, scales,
         ent = _pinned_slots(di)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev)
-            if _ASYNC:
+            capturing = torch.cuda.is_current_stream_capturing()
+            if _ASYNC and not capturing:
                 _drain_pending(ent, di)
             capacity = _initial_capacity(P, W, H, di)
             lib.fs_set_tile_hint(int(_tile_hint.get(key, 0) * 1.25))
-            while True:
+            while capturing:
+                # CUDA-graph capture (fateavatar_b200.graph): the launches are recorded, not run, so nothing can be
+                # waited for.  The frame gets a generous fixed capacity and its own pinned header, which every
+                # replay refreshes; CapturedStep.check() reads it after a replay and raises on overflow.
+                capacity = max(capacity, (2 * int(_capacity_hint.get(key, 0)) + 1023) // 1024 * 1024)
+                nbytes = lib.fs_workspace_bytes(P, W, H, capacity)
+                workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                if not _capture_header_pool:
+                    raise FateSplatError("CUDA-graph capture needs pinned headers reserved beforehand "
+                                         "(use fateavatar_b200.graph.CapturedStep, or reserve_capture_headers())")
+                header = _capture_header_pool.pop()  # pinned memory cannot be allocated while capturing
+                capture_headers.append((header, key, capacity))
+                rc = lib.fs_forward(P, D, M, _ptr(bg), W, H, _ptr(m3), _ptr(sh_c), _ptr(cp_c), _ptr(op_c),
+                                    _ptr(sc_c), float(rs.scale_modifier), _ptr(ro_c), _ptr(c3_c), _ptr(view),
+                                    _ptr(proj), _ptr(campos), float(rs.tanfovx), float(rs.tanfovy),
+                                    int(bool(rs.prefiltered)), color.data_ptr(), radii.data_ptr(),
+                                    workspace.data_ptr(), nbytes, capacity, header.data_ptr(), stream.cuda_stream)
+                _lib.check(rc, "fs_forward")
+                launches += lib.fs_last_launch_count()
+                num_rendered = -1
+                break
+            while not capturing:
                 nbytes = lib.fs_workspace_bytes(P, W, H, capacity)
                 workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
                 slot = ent["next"]
@@ -264,7 +294,7 @@ def backward_raw(state, grad_out_color, out=None):
         dpix = grad_out_color.contiguous()
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev)
-            if _ASYNC:
+            if _ASYNC and not torch.cuda.is_current_stream_capturing():
                 di = dev.index if dev.index is not None else torch.cuda.current_device()
                 _drain_pending(_pinned_slots(di), di, block=True)  # the frame must not have overflowed
             rc = lib.fs_backward(P, D, M, _ptr(bg), W, H, _ptr(m3), _ptr(sh_c), _ptr(cp_c), _ptr(sc_c),

@@ -320,3 +320,53 @@ def test_wrong_tile_hint_only_costs_speed(cuda_device):
         R._tile_hint[key] = hint
         color, radii, st, taps, _ = run_new(sc, cuda_device)
         check_forward_vs_oracle(color, radii, st, taps, o)
+
+
+def test_captured_step_replays_whole_frame_identically(cuda_device):
+    """fateavatar_b200.graph.CapturedStep: a frame (pose stage + rasterizer + L1 loss + backward) recorded into a
+    CUDA graph and replayed on new inputs gives the same image, loss and gradients as the eager operators."""
+    from fateavatar_b200 import graph, pose
+
+    p = scenes.pose_inputs(N=20000, seed=3)
+    cam = scenes.make_camera(160, 128, 0.35, 0.35, T=[0, 0, 1.25])
+    d = lambda a: torch.from_numpy(a).to(cuda_device)
+    faces, fi, bary = d(p["faces"]), d(p["face_index"]), d(p["bary"])
+    from oracle import pose_oracle as po
+    _, canon = po.compute_face_orientation(d(p["canon_verts"]), faces)
+    canon = canon.reshape(-1).contiguous()
+    leaves = [d(p[k]).requires_grad_(True) for k in ("scaling_raw", "rotation_raw", "offset_raw", "opacity_raw")]
+    shs = d(((np.random.default_rng(0).uniform(0, 1, (20000, 1, 3)) - 0.5) / scenes.SH_C0).astype(np.float32)).requires_grad_(True)
+    bg = torch.ones(3, device=cuda_device)
+    view, proj, campos = d(cam["viewmatrix"]), d(cam["projmatrix"]), d(cam["campos"])
+
+    def frame(inp):
+        xyz, sc, ro, op = pose.pose_splats(inp["verts"], faces, fi, bary, canon, *leaves, shell_len=p["shell_len"])
+        rs = R.GaussianRasterizationSettings(128, 160, cam["tanfovx"], cam["tanfovy"], bg, 1.0, view, proj, 0, campos, False, False)
+        img, radii = R.GaussianRasterizer(rs)(means3D=xyz, means2D=torch.zeros_like(xyz, requires_grad=True), shs=shs,
+                                              opacities=op, scales=sc, rotations=ro)
+        loss = (img - inp["target"]).abs().mean()
+        loss.backward()
+        return {"loss": loss.detach().reshape(1), "image": img.detach()}
+
+    g = torch.Generator().manual_seed(0)
+    mk = lambda seed: {"verts": torch.from_numpy(scenes.pose_inputs(N=1, seed=seed)["verts"]).pin_memory(),
+                       "target": torch.rand(3, 128, 160, generator=g).pin_memory()}
+    step = graph.CapturedStep(frame, {k: v.to(cuda_device) for k, v in mk(3).items()}, params=leaves + [shs])
+    for seed in (4, 5):
+        batch = mk(seed)
+        out = step(batch)
+        step.wait()
+        got = {k: v.clone() for k, v in out.items()}
+        got_grads = [g_.clone() for g_ in step.grads]
+        assert all(q.grad is g_ for q, g_ in zip(leaves + [shs], step.grads))
+        assert step.num_rendered()[0] > 0
+        for q in leaves + [shs]:
+            q.grad = None
+        ref = frame({k: v.to(cuda_device) for k, v in batch.items()})
+        torch.cuda.synchronize()
+        assert torch.equal(got["image"], ref["image"].cpu())
+        assert abs(float(got["loss"]) - float(ref["loss"])) <= 1e-7
+        for a, q in zip(got_grads, leaves + [shs]):
+            assert float((a - q.grad).abs().max()) <= 2e-4 * float(q.grad.abs().max())  # float atomics order
+        for q, g_ in zip(leaves + [shs], step.grads):
+            q.grad = g_  # re-attach the tensors the replay writes
