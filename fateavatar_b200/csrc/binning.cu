@@ -150,15 +150,40 @@ scatter_kernel(int P, int gx, const ushort4* __restrict__ rect, const float* __r
     fs::pdl_trigger();
     fs::pdl_wait();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
-    const ushort4 rc = rect[idx];
-    if (rc.x >= rc.z || rc.y >= rc.w) return;
-    const u64 key = ((u64)__float_as_uint(depths[idx]) << 32) | (uint32_t)idx;
-    for (int y = rc.y; y < rc.w; ++y)
-        for (int x = rc.x; x < rc.z; ++x) {
+    const int lane = threadIdx.x & 31;
+    ushort4 rc = make_ushort4(0, 0, 0, 0);
+    u64 key = 0;
+    if (idx < P) {
+        rc = rect[idx];
+        key = ((u64)__float_as_uint(depths[idx]) << 32) | (uint32_t)idx;
+    }
+    const int w = max(0, (int)rc.z - (int)rc.x), h = max(0, (int)rc.w - (int)rc.y);
+    const int count = w * h;
+    // A splat that covers many tiles would make its thread the tail of the whole kernel (one returning atomic per
+    // tile, serially): such rectangles are handed to the warp, 32 tiles per round; small ones stay with their lane.
+    constexpr int kOwnMax = 32;
+    if (count <= kOwnMax) {
+        for (int y = rc.y; y < rc.w; ++y)
+            for (int x = rc.x; x < rc.z; ++x) {
+                const uint32_t pos = atomicAdd(&tile_cursor[(size_t)(y * gx + x) * FS_CNT_STRIDE], 1u);
+                if (pos < Rcap) keys[pos] = key;
+            }
+    }
+    unsigned big = __ballot_sync(0xffffffffu, count > kOwnMax);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const int bx0 = __shfl_sync(0xffffffffu, (int)rc.x, src), by0 = __shfl_sync(0xffffffffu, (int)rc.y, src);
+        const int bw = __shfl_sync(0xffffffffu, w, src), bn = __shfl_sync(0xffffffffu, count, src);
+        const uint32_t klo = __shfl_sync(0xffffffffu, (uint32_t)key, src);
+        const uint32_t khi = __shfl_sync(0xffffffffu, (uint32_t)(key >> 32), src);
+        const u64 bkey = ((u64)khi << 32) | klo;
+        for (int t = lane; t < bn; t += 32) {
+            const int y = by0 + t / bw, x = bx0 + t % bw;
             const uint32_t pos = atomicAdd(&tile_cursor[(size_t)(y * gx + x) * FS_CNT_STRIDE], 1u);
-            if (pos < Rcap) keys[pos] = key;
+            if (pos < Rcap) keys[pos] = bkey;
         }
+    }
 }
 
 // ---- bitonic network with ascending-only compare-exchanges (virtual +inf padding needs no storage) --------

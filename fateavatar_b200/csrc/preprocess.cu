@@ -96,8 +96,9 @@ preprocess_kernel(int P, int D, int M, const float* __restrict__ means3D, const 
     __syncthreads();
 
     bool visible = false;
+    int4 hist = make_int4(0, 0, 0, 0);  // tile rectangle this lane adds to the per-tile histogram
+    const int gx = (W + FS_TILE - 1) / FS_TILE, gy = (H + FS_TILE - 1) / FS_TILE;
     if (idx < P) {
-        const int gx = (W + FS_TILE - 1) / FS_TILE, gy = (H + FS_TILE - 1) / FS_TILE;
         const float px = s_xyz[3 * threadIdx.x], py = s_xyz[3 * threadIdx.x + 1], pz = s_xyz[3 * threadIdx.x + 2];
         int radius = 0;
         uint32_t ntiles = 0;
@@ -188,8 +189,7 @@ preprocess_kernel(int P, int D, int M, const float* __restrict__ means3D, const 
                     rec.q2 = make_float4(r, g, b, __uint_as_float((uint32_t)idx));
                     splat[idx] = rec;
                     clamped[idx] = cl;
-                    for (int y = y0; y < y1; ++y)
-                        for (int x = x0; x < x1; ++x) atomicAdd(&tile_count[(size_t)(y * gx + x) * FS_CNT_STRIDE], 1u);
+                    hist = make_int4(x0, y0, x1, y1);
                 }
             }
         } else if (prefiltered) {
@@ -198,6 +198,23 @@ preprocess_kernel(int P, int D, int M, const float* __restrict__ means3D, const 
         radii[idx] = radius;
         tiles_touched[idx] = ntiles;
         rect[idx] = rc;
+    }
+    {   // per-tile instance histogram; rectangles of many tiles are spread over the warp (see scatter_kernel)
+        const int hw = hist.z - hist.x, cnt = hw * (hist.w - hist.y);
+        constexpr int kOwnMax = 32;
+        if (cnt <= kOwnMax)
+            for (int y = hist.y; y < hist.w; ++y)
+                for (int x = hist.x; x < hist.z; ++x) atomicAdd(&tile_count[(size_t)(y * gx + x) * FS_CNT_STRIDE], 1u);
+        unsigned big = __ballot_sync(0xffffffffu, cnt > kOwnMax);
+        const int lane = threadIdx.x & 31;
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            const int bx0 = __shfl_sync(0xffffffffu, hist.x, src), by0 = __shfl_sync(0xffffffffu, hist.y, src);
+            const int bw = __shfl_sync(0xffffffffu, hw, src), bn = __shfl_sync(0xffffffffu, cnt, src);
+            for (int t = lane; t < bn; t += 32)
+                atomicAdd(&tile_count[(size_t)((by0 + t / bw) * gx + bx0 + t % bw) * FS_CNT_STRIDE], 1u);
+        }
     }
     const unsigned vmask = __ballot_sync(0xffffffffu, visible);
     if ((threadIdx.x & 31) == 0 && vmask) atomicAdd(&info->num_visible, (uint32_t)__popc(vmask));
