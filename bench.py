@@ -64,8 +64,8 @@ def workload_config(args):
                         f"FLAME lbs + pose + render forward + backward (to splat parameters and FLAME deltas) per frame",
             "frames_in_ring": N_RING,
             "l2_policy": f"ring of {N_RING} distinct frames (inputs+workspaces ~45 MB each > 126 MB L2 in total)",
-            "parallelism": f"frames sharded one per GPU (dp{args.gpus}); one NCCL all-reduce per step over the splat "
-                           f"gradients + the rank-1 factors of the FLAME delta gradients (expanded locally)"}
+            "parallelism": f"frames sharded one per GPU (dp{args.gpus}); per step one exchange of the flat gradient bucket "
+                           f"(splat gradients + rank-1 factors of the FLAME delta gradients, expanded locally)"}
 
 
 FLAME_KEYS = ("v_template", "shapedirs", "posedirs", "J_regressor", "lbs_weights")
@@ -281,22 +281,38 @@ def main():
     from fateavatar_b200 import flame
 
     rec_n = flame.factor_record_floats(V, L, NPF)
-    bucket = torch.zeros(15 * P + world * rec_n, device=dev)
-    scratch = torch.zeros(11 * P, device=dev)
+    n_bucket = 15 * P + world * rec_n
     # bucket = [A: SH 3P, screen-space statistic 3P | B: scaling 3P, rotation 4P, offset P, opacity P | C: factors]
-    # A is complete after the rasterizer backward, B after the pose backward, C after the FLAME backward: each part
-    # is all-reduced asynchronously as soon as it exists, so A and B travel while the rest of the backward runs
-    # (what DDP does with its buckets) and only the small factor exchange is exposed.
-    rv = dict(means3D=scratch[0:3 * P], scales=scratch[3 * P:6 * P], rotations=scratch[6 * P:10 * P],
-              opacity=scratch[10 * P:11 * P], sh=bucket[0:3 * P], means2D=bucket[3 * P:6 * P])
+    # Exchange (N > 1), FATESPLAT_BENCH_EXCHANGE:
+    #   p2p (default)  the bucket lives in symmetric peer-mapped memory (two buffers used alternately); one barrier
+    #                  + ONE kernel (fs_p2p_allreduce: multimem.ld_reduce through the NVLink switch, or unicast peer
+    #                  loads) gives every rank the sum -- no NCCL call in the step
+    #   nccl           one NCCL all-reduce over the bucket
+    #   overlap        three asynchronous NCCL all-reduces (A, B, C) overlapped with the backward (measured slower)
+    mode = os.environ.get("FATESPLAT_BENCH_EXCHANGE", "p2p") if dist is not None else "none"
+    sym = None
+    if mode == "p2p":
+        try:
+            from fateavatar_b200.exchange import SymmetricBucket
+
+            sym = SymmetricBucket(n_bucket, dev)
+        except Exception as ex:  # e.g. no peer access between the visible devices
+            mode = f"nccl (symmetric memory unavailable: {repr(ex)[:120]})"
+    buckets = [sym.local(0), sym.local(1)] if sym is not None else [torch.zeros(n_bucket, device=dev)] * 2
+    scratch = torch.zeros(11 * P, device=dev)
     d_verts = torch.empty(V, 3, device=dev)
-    pv = (d_verts, bucket[6 * P:9 * P].view(P, 3), bucket[9 * P:13 * P].view(P, 4),
-          bucket[13 * P:14 * P].view(P, 1), bucket[14 * P:15 * P].view(P, 1))
-    part_a, part_b, part_c = bucket[:6 * P], bucket[6 * P:15 * P], bucket[15 * P:]
+
+    def views(bucket):
+        rv = dict(means3D=scratch[0:3 * P], scales=scratch[3 * P:6 * P], rotations=scratch[6 * P:10 * P],
+                  opacity=scratch[10 * P:11 * P], sh=bucket[0:3 * P], means2D=bucket[3 * P:6 * P])
+        pv = (d_verts, bucket[6 * P:9 * P].view(P, 3), bucket[9 * P:13 * P].view(P, 4),
+              bucket[13 * P:14 * P].view(P, 1), bucket[14 * P:15 * P].view(P, 1))
+        gathered = bucket[15 * P:15 * P + world * rec_n].view(world, rec_n)
+        return dict(rv=rv, pv=pv, a=bucket[:6 * P], b=bucket[6 * P:15 * P], c=bucket[15 * P:n_bucket], all=bucket[:n_bucket],
+                    gathered=gathered, record=gathered[rank], others=[gathered[r] for r in range(world) if r != rank])
+
+    bviews = [views(buckets[0]), views(buckets[1])]
     fgrads = [torch.empty(V, 3, device=dev), torch.empty(V, 3, L, device=dev), torch.empty(NPF, 3 * V, device=dev)]
-    gathered = bucket[15 * P:].view(world, rec_n)
-    record = gathered[rank]
-    others = [gathered[r] for r in range(world) if r != rank]
     pose_out = [(torch.empty(P, 3, device=dev), torch.empty(P, 3, device=dev), torch.empty(P, 4, device=dev),
                  torch.empty(P, 1, device=dev)) for _ in range(N_RING)]
     fl_out = [flame.flame_forward_raw(betas[k], fpose[k], fmodel["v_template"], fmodel["shapedirs"], fmodel["posedirs"],
@@ -308,10 +324,16 @@ def main():
     ring = [None] * N_RING
     launches = [0]
 
-    overlap = os.environ.get("FATESPLAT_BENCH_EXCHANGE", "single") == "overlap"
+    overlap = mode == "overlap"
+
+    tick = [0]  # steps issued so far: consecutive steps alternate between the two bucket buffers
 
     def step(i):
         k = i % N_RING
+        t_ = tick[0]
+        tick[0] += 1
+        bv = bviews[t_ & 1]
+        rv, pv, record = bv["rv"], bv["pv"], bv["record"]
         fo_ = flame.flame_forward_raw(betas[k], fpose[k], fmodel["v_template"], fmodel["shapedirs"], fmodel["posedirs"],
                                       fmodel["J_regressor"], fmodel["parents"], fmodel["lbs_weights"],
                                       fdelta["delta_vertex"], fdelta["delta_shapedirs"], fdelta["delta_posedirs"],
@@ -322,27 +344,30 @@ def main():
         color, radii, st = R.forward_raw(rs, xyz, shs, None, op, sc, ro, None)
         R.backward_raw(st, dpix[k], out=rv)
         exchange = dist is not None and not args.no_collective
-        wa = dist.all_reduce(part_a, async_op=True) if exchange and overlap else None
-        pose.pose_backward_raw(verts_k, faces, fidx, bary, canon, *params, rv["means3D"].view(P, 3),
-                               rv["scales"].view(P, 3), rv["rotations"].view(P, 4), rv["opacity"].view(P, 1),
-                               shell_len=f0["shell_len"], out=pv)
+        wa = dist.all_reduce(bv["a"], async_op=True) if exchange and overlap else None
+        pose.pose_backward_raw(verts_k, faces, fidx, bary, canon, *params, scratch[0:3 * P].view(P, 3),
+                               scratch[3 * P:6 * P].view(P, 3), scratch[6 * P:10 * P].view(P, 4),
+                               scratch[10 * P:11 * P].view(P, 1), shell_len=f0["shell_len"], out=pv)
         if not exchange:
             flame.flame_backward_raw(betas[k], fmodel["J_regressor"], fmodel["parents"], fmodel["lbs_weights"],
                                      fo_["workspace"], d_verts, (V, L), l0=n_shape, out=fgrads)
         else:
-            wb = dist.all_reduce(part_b, async_op=True) if overlap else None
+            wb = dist.all_reduce(bv["b"], async_op=True) if overlap else None
             # the FLAME delta gradients are rank-1 per frame: exchange their factors (~120 KB per rank; every rank
-            # fills its own slot of part C, the others are zero, so the sum all-reduce is the all-gather) and expand
-            # the sum locally instead of all-reducing 26 MB
-            for o_ in others:
-                o_.zero_()
-            record[:L].copy_(betas[k])
-            record[L:L + NPF].copy_(fo_["pose_feature"])
+            # fills its own slot of part C, the others are zero, so the sum is the all-gather) and expand the sum
+            # locally instead of all-reducing 26 MB
+            if sym is None:  # (in p2p mode the sum never lands in the bucket, so the other slots stay zero)
+                for o_ in bv["others"]:
+                    o_.zero_()
             flame.flame_backward_raw(betas[k], fmodel["J_regressor"], fmodel["parents"], fmodel["lbs_weights"],
                                      fo_["workspace"], d_verts, (V, L), l0=n_shape, want=(False, False, False),
-                                     factor_out=(record[L + NPF:L + NPF + 3 * V].view(V, 3),
-                                                 record[L + NPF + 3 * V:L + NPF + 6 * V].view(V, 3)))
-            dist.all_reduce(part_c if overlap else bucket)
+                                     record=record)
+            if sym is not None:
+                summed = sym.all_reduce(t_, n_bucket)  # rank-local sum of every rank's bucket
+                gathered = summed[15 * P:15 * P + world * rec_n].view(world, rec_n)
+            else:
+                dist.all_reduce(bv["c"] if overlap else bv["all"])
+                gathered = bv["gathered"]
             flame.expand_factors(gathered, V, L, NPF, l0=n_shape, out=fgrads)
             if overlap:
                 wa.wait()
@@ -594,7 +619,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(args), "num_rendered": Rn, "clocks": sampler.summary(), "e2e": e2e,
+                "config": dict(workload_config(args), exchange=mode), "num_rendered": Rn, "clocks": sampler.summary(), "e2e": e2e,
                 "gpu_launches": launches[0] * args.steps, "gpu_launches_per_step": launches[0], "roofline": roofline,
                 "kernels": kernels, "cpu_baseline": cb, "gpu_reference": gpu_ref,
                 "speedup_vs_gpu_reference": (value / world / gpu_ref["value"]) if gpu_ref and "value" in gpu_ref else None}

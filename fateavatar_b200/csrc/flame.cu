@@ -382,7 +382,7 @@ flame_blend_backward_kernel(int V, int L, int l0, int J, Parents parents, int nb
                             const FlameState* __restrict__ state, const float* __restrict__ g_posed,
                             const float* __restrict__ dapart, float* __restrict__ d_delta_vertex,
                             float* __restrict__ d_delta_shapedirs, float* __restrict__ d_delta_posedirs,
-                            float* __restrict__ d_v_shaped) {
+                            float* __restrict__ d_v_shaped, float* __restrict__ factor_header /*[L + NP] or null*/) {
     __shared__ float s_dA[kMaxJ][12];
     __shared__ float s_dJ[kMaxJ][3], s_dRg[kMaxJ][9], s_dtg[kMaxJ][3];
     __shared__ FlameState S;  // forward state (joints, rotations, chain): one round trip instead of one per use
@@ -436,6 +436,10 @@ flame_blend_backward_kernel(int V, int L, int l0, int J, Parents parents, int nb
     }
     __syncthreads();
 
+    if (factor_header && blockIdx.x == 0) {  // [betas | pose_feature]: the head of this rank's factor record
+        for (int i = t; i < L; i += kBlendBwdThreads) factor_header[i] = i >= l0 ? __ldg(betas + i) : 0.0f;
+        for (int i = t; i < NP; i += kBlendBwdThreads) factor_header[L + i] = S.pf[i];
+    }
     // rank-1 gradient of delta_posedirs: pose_feature (x) dL/dv_posed, coalesced along the coordinate axis
     if (d_delta_posedirs) {
         const int nthreads = gridDim.x * kBlendBwdThreads;
@@ -629,7 +633,7 @@ int fs_flame_backward(int V, int L, int l0, int J, const int* parents_host, cons
                       const float* d_J_regressor, const float* d_lbs_weights, const float* d_dL_dverts,
                       void* d_workspace, size_t workspace_bytes, float* d_dL_ddelta_vertex,
                       float* d_dL_ddelta_shapedirs, float* d_dL_ddelta_posedirs, float* d_dL_dv_shaped,
-                      float* d_dL_dv_posed, void* stream) {
+                      float* d_dL_dv_posed, float* d_factor_header, void* stream) {
     Parents P;
     if (V <= 0 || L <= 0 || l0 < 0 || l0 > L || !parents_ok(J, parents_host, P)) {
         fs_set_error("fs_flame_backward: invalid size or kinematic tree");
@@ -662,7 +666,7 @@ int fs_flame_backward(int V, int L, int l0, int J, const int* parents_host, cons
     fs_launch_pdl(flame_blend_backward_kernel, dim3(grid), dim3(kBlendBwdThreads), 0, st, V, L, l0, J, P, w.nblk_skin,
                   d_betas, d_J_regressor, reinterpret_cast<const FlameState*>(ws + w.state),
                   (const float*)g_posed, reinterpret_cast<const float*>(ws + w.dapart), d_dL_ddelta_vertex,
-                  d_dL_ddelta_shapedirs, d_dL_ddelta_posedirs, d_dL_dv_shaped);
+                  d_dL_ddelta_shapedirs, d_dL_ddelta_posedirs, d_dL_dv_shaped, d_factor_header);
     fs_count_launch(2);
     if (cudaGetLastError() != cudaSuccess) {
         fs_set_error("fs_flame_backward: launch failed");

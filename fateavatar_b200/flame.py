@@ -69,11 +69,12 @@ def flame_forward_raw(betas, pose, v_template, shapedirs, posedirs, J_regressor,
 
 
 def flame_backward_raw(betas, J_regressor, parents, lbs_weights, workspace, dL_dverts, shapes, l0=0,
-                       want=(True, True, True), out=None, factors=False, factor_out=None):
+                       want=(True, True, True), out=None, factors=False, factor_out=None, record=None):
     """One fs_flame_backward call.  `shapes` = (V, L); `want` selects (delta_vertex, delta_shapedirs,
     delta_posedirs) gradients; `out` may supply preallocated tensors for them.  With factors=True also returns
     (dL_dv_shaped, dL_dv_posed), the [V,3] factors of the two rank-1 gradients (written into `factor_out` when
-    given, e.g. views of an all-gather record)."""
+    given, e.g. views of an all-gather record).  `record` (a flat factor record, see factor_record_floats) makes the
+    call fill this rank's whole record in place: [betas | pose_feature | dL_dv_shaped | dL_dv_posed]."""
     lib = _lib.load()
     dev = dL_dverts.device
     V, L = shapes
@@ -85,6 +86,11 @@ def flame_backward_raw(betas, J_regressor, parents, lbs_weights, workspace, dL_d
         o[1] = torch.empty((V, 3, L), device=dev)
     if want[2] and o[2] is None:
         o[2] = torch.empty(((J - 1) * 9, V * 3), device=dev)
+    header = None
+    if record is not None:
+        NPr = (J - 1) * 9
+        header = record
+        factor_out = (record[L + NPr:L + NPr + 3 * V], record[L + NPr + 3 * V:L + NPr + 6 * V])
     if factor_out is not None:
         gs, gp = factor_out
         factors = True
@@ -95,7 +101,7 @@ def flame_backward_raw(betas, J_regressor, parents, lbs_weights, workspace, dL_d
         rc = lib.fs_flame_backward(V, L, int(l0), J, pc, betas.data_ptr(), J_regressor.data_ptr(), lbs_weights.data_ptr(),
                                    dL_dverts.data_ptr(), workspace.data_ptr(), workspace.numel(),
                                    _ptr(o[0]) if want[0] else None, _ptr(o[1]) if want[1] else None,
-                                   _ptr(o[2]) if want[2] else None, _ptr(gs), _ptr(gp),
+                                   _ptr(o[2]) if want[2] else None, _ptr(gs), _ptr(gp), _ptr(header),
                                    torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "fs_flame_backward")
     return (o[0], o[1], o[2]) + ((gs, gp) if factors else ())

@@ -177,7 +177,9 @@ int fs_pose_backward(int N, int V, int F, const float* d_verts, const long long*
  * Backward: dL/dverts [V,3] -> dL/d{delta_vertex, delta_shapedirs, delta_posedirs} (each optional), including the
  * path through the joint regression and the kinematic chain.  d_dL_dv_shaped / d_dL_dv_posed (optional, [V,3])
  * expose the factors of the two rank-1 gradients (delta_shapedirs grad = dL_dv_shaped (x) betas, delta_posedirs
- * grad = pose_feature (x) dL_dv_posed) for callers that all-reduce 62 KB instead of 26 MB.
+ * grad = pose_feature (x) dL_dv_posed) for callers that all-reduce 62 KB instead of 26 MB;
+ * d_factor_header (optional, [L + (J-1)*9]) receives [betas | pose_feature], the head of the factor record of
+ * fs_flame_expand_grads, so a rank's whole record is produced by this one call.
  * Gradients w.r.t. betas and pose are not produced (FateAvatar does not optimise them on INSTA data).
  */
 #define FS_FLAME_MAX_JOINTS 8
@@ -192,7 +194,7 @@ int fs_flame_backward(int V, int L, int l0, int J, const int* parents_host, cons
                       const float* d_J_regressor, const float* d_lbs_weights, const float* d_dL_dverts,
                       void* d_workspace, size_t workspace_bytes, float* d_dL_ddelta_vertex,
                       float* d_dL_ddelta_shapedirs, float* d_dL_ddelta_posedirs, float* d_dL_dv_shaped,
-                      float* d_dL_dv_posed, void* stream);
+                      float* d_dL_dv_posed, float* d_factor_header, void* stream);
 
 /*
  * Data-parallel exchange of the FLAME delta gradients in factored form.  Each rank's
@@ -206,6 +208,22 @@ int fs_flame_backward(int V, int L, int l0, int J, const int* parents_host, cons
 int fs_flame_expand_grads(int N, int V, int L, int l0, int NP, const float* d_factors, size_t rank_stride, float scale,
                           float* d_dL_ddelta_vertex, float* d_dL_ddelta_shapedirs, float* d_dL_ddelta_posedirs,
                           void* stream);
+
+/*
+ * Peer-memory all-reduce (sum) of the frame-sharded step's flat gradient bucket, one kernel over
+ * NVLink / NVSwitch instead of an NCCL call.  Every rank holds `n` floats (a multiple of 4, 16-byte aligned) at the
+ * same offset of a symmetric, peer-mapped allocation (e.g. torch.distributed._symmetric_memory):
+ *   d_multicast != NULL : multicast address of that region; the NVLink switch adds the N copies in flight
+ *                         (multimem.ld_reduce), so a rank reads n floats once regardless of N;
+ *   otherwise           : d_peer_ptrs, a DEVICE array of the N ranks' unicast addresses, summed in rank order
+ *                         (bitwise identical result on every rank).
+ * `offset` (floats, multiple of 4) is added to every base address: one allocation can hold several buckets.
+ * The sum is written to the rank-local d_out (must not alias the symmetric region).  The caller puts a cross-rank
+ * barrier before the call (all buckets complete) and keeps every rank from refilling a bucket that others may
+ * still be reading (a second barrier, or two buckets used alternately).
+ */
+int fs_p2p_allreduce(int N, const float* d_multicast, const float* const* d_peer_ptrs, size_t offset, size_t n,
+                     float* d_out, void* stream);
 
 /*
  * Densification statistics (model/fateavatar.py:734-737, gaussian_model.py:418-420), in place:

@@ -90,7 +90,7 @@ def test_flame_abi_rejects_bad_arguments_without_touching_the_gpu():
     assert lib.fs_flame_forward(0, 8, 0, 5, ok_tree, *nul, None, 0, None) == -1
     assert lib.fs_flame_forward(10, 8, 9, 5, ok_tree, *nul, None, 0, None) == -1          # l0 > L
     assert lib.fs_flame_forward(10, 8, 0, 9, ok_tree, *nul, None, 0, None) == -1          # J > FS_FLAME_MAX_JOINTS
-    assert lib.fs_flame_backward(10, 8, 0, 5, bad_tree, None, None, None, None, None, 0, None, None, None, None, None, None) == -1
+    assert lib.fs_flame_backward(10, 8, 0, 5, bad_tree, None, None, None, None, None, 0, None, None, None, None, None, None, None) == -1
     assert lib.fs_flame_workspace_bytes(0) == 0
 
 
@@ -239,3 +239,8 @@ def test_expand_factors_kernel_and_single_rank_identity(cuda_device):
     flame.pack_factors(record[0], t("betas"), r["pose_feature"], gs, gp)
     ev, es, ep = flame.expand_factors(record, 200, 400, 36, l0=300)
     assert torch.equal(ev, dv) and torch.equal(es, ds) and torch.equal(ep, dp)
+    # the same record produced in place by one fs_flame_backward call
+    rec2 = torch.zeros_like(record)
+    flame.flame_backward_raw(t("betas"), m["J_regressor"], m["parents"], m["lbs_weights"], r["workspace"], up, (200, 400),
+                             l0=300, want=(False, False, False), record=rec2[0])
+    assert torch.equal(rec2, record)
