@@ -36,6 +36,27 @@ p2p_allreduce_multicast_kernel(const float* __restrict__ mc, size_t n4, float4* 
     for (; i < n4; i += stride) out[i] = multimem_ld_reduce_add(mc + 4 * i);
 }
 
+__device__ __forceinline__ void multimem_st(float* mc, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+
+// Two-shot all-reduce through the switch: this rank owns the float4 range [lo, hi) of the bucket, pulls its sum over
+// all ranks with one in-switch reduction and pushes the result into EVERY rank's output with one multicast store.
+// Per rank n/N floats cross the link in each direction, independent of N (the one-shot kernel moves n).
+__global__ void __launch_bounds__(512)
+p2p_reduce_scatter_bcast_kernel(const float* __restrict__ mc_in, float* __restrict__ mc_out, size_t lo, size_t hi) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < hi; i += 2 * stride) {
+        const float4 a = multimem_ld_reduce_add(mc_in + 4 * i), b = multimem_ld_reduce_add(mc_in + 4 * (i + stride));
+        multimem_st(mc_out + 4 * i, a);
+        multimem_st(mc_out + 4 * (i + stride), b);
+    }
+    for (; i < hi; i += stride) multimem_st(mc_out + 4 * i, multimem_ld_reduce_add(mc_in + 4 * i));
+}
+
 __global__ void __launch_bounds__(512)
 p2p_allreduce_unicast_kernel(int N, const float* const* __restrict__ peers, size_t offset, size_t n4,
                              float4* __restrict__ out) {
@@ -81,6 +102,27 @@ extern "C" int fs_p2p_allreduce(int N, const float* d_multicast, const float* co
     fs_count_launch(1);
     if (cudaGetLastError() != cudaSuccess) {
         fs_set_error("fs_p2p_allreduce: launch failed");
+        return FS_ERR_CUDA;
+    }
+    return FS_OK;
+}
+
+extern "C" int fs_p2p_reduce_scatter_bcast(int N, int rank, const float* d_multicast_in, float* d_multicast_out,
+                                           size_t n, void* stream) {
+    if (N < 1 || N > FS_FLAME_MAX_RANKS || rank < 0 || rank >= N || (n & 3) != 0 || !d_multicast_in || !d_multicast_out) {
+        fs_set_error("fs_p2p_reduce_scatter_bcast: invalid argument (1 <= N <= %d, 0 <= rank < N, n a multiple of 4, "
+                     "multicast addresses of the input and output regions)", FS_FLAME_MAX_RANKS);
+        return FS_ERR_INVALID_ARGUMENT;
+    }
+    const size_t n4 = n / 4, per = (n4 + N - 1) / N;
+    const size_t lo = std::min(n4, per * (size_t)rank), hi = std::min(n4, lo + per);
+    if (hi == lo) return FS_OK;
+    const int grid = (int)std::min<size_t>((hi - lo + 511) / 512, (size_t)fs_num_sms());
+    p2p_reduce_scatter_bcast_kernel<<<grid, 512, 0, static_cast<cudaStream_t>(stream)>>>(d_multicast_in, d_multicast_out,
+                                                                                         lo, hi);
+    fs_count_launch(1);
+    if (cudaGetLastError() != cudaSuccess) {
+        fs_set_error("fs_p2p_reduce_scatter_bcast: launch failed");
         return FS_ERR_CUDA;
     }
     return FS_OK;

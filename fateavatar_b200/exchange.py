@@ -8,7 +8,9 @@
 
 The buckets live in torch's symmetric memory (CUDA VMM, peer-mapped; multicast-bound when the box has
 NVSwitch/NVLS); `fs_p2p_allreduce` reads the sum of the N copies with multimem.ld_reduce (or N unicast peer loads).
-Synchronisation is one symmetric-memory signal-pad barrier per step: it proves every rank has finished writing the
+From 4 ranks on the two-shot form takes over (fs_p2p_reduce_scatter_bcast: each rank reduces its 1/N slice in the
+switch and multicast-stores it to all ranks, n/N floats per rank on the wire, one more barrier).
+Synchronisation of the one-shot form is one symmetric-memory signal-pad barrier per step: it proves every rank has finished writing the
 bucket of step s, and -- because consecutive steps use different buffers -- by the time a rank refills buffer
 s % 2 at step s + 2 every rank has passed the barrier of step s + 1, i.e. has finished reading it.  No NCCL call
 sits in the step.
@@ -22,7 +24,11 @@ from ._lib import FateSplatError
 
 
 class SymmetricBucket:
-    def __init__(self, n_floats, device, group=None, use_multicast=None):
+    """algo: "one_shot" (every rank reads the sum of all copies: unicast peer loads or, `use_multicast`, in-switch
+    reduction), "two_shot" (each rank reduces its 1/N slice in the switch and multicast-stores it to everybody; two
+    barriers, n/N floats per rank on the wire) or None = pick by world size."""
+
+    def __init__(self, n_floats, device, group=None, use_multicast=None, algo=None):
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
 
@@ -30,19 +36,29 @@ class SymmetricBucket:
             raise FateSplatError("SymmetricBucket needs an initialised torch.distributed process group")
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
         self.n = (int(n_floats) + 63) // 64 * 64
         self.device = torch.device(device)
-        self.both = symm.empty(2 * self.n, dtype=torch.float32, device=self.device)
+        # [ input buffer of even steps | input buffer of odd steps | output of the two-shot algorithm ]
+        self.both = symm.empty(3 * self.n, dtype=torch.float32, device=self.device)
         self.both.zero_()
         self.hdl = symm.rendezvous(self.both, self.group)
-        self.out = torch.empty(self.n, dtype=torch.float32, device=self.device)
+        self.out_local = torch.empty(self.n, dtype=torch.float32, device=self.device)
+        mc_base = int(self.hdl.multicast_ptr)
+        if algo is None:
+            # measured on B200 / NVLink 5 at 6.2 MB: N = 2: 23 us one-shot unicast, 31 us one-shot multicast;
+            # N = 8: 85 / 83 us one-shot (NCCL 58 us) -> the two-shot algorithm takes over from 4 ranks
+            algo = os.environ.get("FATESPLAT_P2P_ALGO", "auto")
+            if algo == "auto":
+                algo = "two_shot" if (self.world >= 4 and mc_base) else "one_shot"
+        if algo == "two_shot" and not mc_base:
+            raise FateSplatError("the two-shot exchange needs NVLink multicast (NVSwitch/NVLS), not available here")
+        self.algo = algo
         if use_multicast is None:
-            # in-switch reduction reads n floats once per rank but each request takes the long way round; plain peer
-            # loads read N copies.  Measured on B200/NVLink5 at 6 MB: N = 2 -> 23 us unicast vs 31 us multicast.
             env = os.environ.get("FATESPLAT_P2P_MULTICAST", "auto")
             use_multicast = self.world >= 4 if env == "auto" else env == "1"
-        mc = int(self.hdl.multicast_ptr) if use_multicast else 0
-        self.multicast_ptr = mc if mc else None
+        self.multicast_base = mc_base if mc_base else None
+        self.multicast_ptr = mc_base if (mc_base and use_multicast) else None
         self.peer_ptrs_dev = int(self.hdl.buffer_ptrs_dev)
         torch.cuda.synchronize(self.device)
         self.hdl.barrier(channel=0)
@@ -53,11 +69,20 @@ class SymmetricBucket:
         return self.both[k * self.n:(k + 1) * self.n]
 
     def all_reduce(self, step, n=None):
-        """Sum over ranks of local(step)[:n] -> out[:n] (rank-local).  Stream-ordered on torch's current stream."""
+        """Sum over ranks of local(step)[:n] -> a rank-local tensor of n floats.  Stream-ordered on torch's current
+        stream."""
         n = self.n if n is None else (int(n) + 3) // 4 * 4
+        lib = _lib.load()
         with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
             self.hdl.barrier(channel=0)  # every rank's bucket of this step is complete and visible
-            rc = _lib.load().fs_p2p_allreduce(self.world, self.multicast_ptr, self.peer_ptrs_dev, (step & 1) * self.n, n,
-                                              self.out.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+            if self.algo == "two_shot":
+                rc = lib.fs_p2p_reduce_scatter_bcast(self.world, self.rank, self.multicast_base + 4 * (step & 1) * self.n,
+                                                     self.multicast_base + 4 * 2 * self.n, n, stream)
+                _lib.check(rc, "fs_p2p_reduce_scatter_bcast")
+                self.hdl.barrier(channel=1)  # every rank's slice has landed in everybody's output region
+                return self.both[2 * self.n:2 * self.n + n]
+            rc = lib.fs_p2p_allreduce(self.world, self.multicast_ptr, self.peer_ptrs_dev, (step & 1) * self.n, n,
+                                      self.out_local.data_ptr(), stream)
             _lib.check(rc, "fs_p2p_allreduce")
-        return self.out[:n]
+        return self.out_local[:n]

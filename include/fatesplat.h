@@ -226,6 +226,15 @@ int fs_p2p_allreduce(int N, const float* d_multicast, const float* const* d_peer
                      float* d_out, void* stream);
 
 /*
+ * Two-shot variant for larger N (needs multicast): rank `rank` reduces ITS 1/N slice of the n floats with one
+ * in-switch reduction (multimem.ld_reduce on d_multicast_in) and broadcasts the result into every rank's output
+ * region with multicast stores (multimem.st on d_multicast_out) -- n/N floats per rank and direction instead of n.
+ * Needs a cross-rank barrier before (inputs complete) AND after (all slices have landed) the call.
+ */
+int fs_p2p_reduce_scatter_bcast(int N, int rank, const float* d_multicast_in, float* d_multicast_out, size_t n,
+                                void* stream);
+
+/*
  * Densification statistics (model/fateavatar.py:734-737, gaussian_model.py:418-420), in place:
  *   xyz_gradient_accum[i] += hypot(viewspace_grad[i,0], viewspace_grad[i,1]);  denom[i] += 1   where update_filter[i]
  * viewspace_grad [P,3] is the .grad of the dummy screen-space tensor (fs_backward's dL_dmeans2D), update_filter [P]

@@ -135,3 +135,29 @@ def test_factored_flame_delta_gradient_exchange_world2():
     assert np.allclose(ds, want["delta_shapedirs"].numpy(), rtol=1e-10, atol=1e-12)
     assert np.allclose(dp, want["delta_posedirs"].numpy(), rtol=1e-9, atol=1e-12)
     assert nrec * 8 < 0.05 * sum(v.numel() for v in want.values()) * 8  # wire record is a few % of the dense gradients
+
+
+@pytest.mark.gpu
+def test_peer_memory_exchange_matches_nccl_on_two_gpus():
+    """fs_p2p_allreduce / fs_p2p_reduce_scatter_bcast over symmetric memory vs NCCL all_reduce (needs >= 2 GPUs)."""
+    import json
+    import subprocess
+    import sys
+
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs with peer access")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(root, "tools", "p2p_check.py")],
+                         capture_output=True, text=True, timeout=600)
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert line, out.stderr[-2000:]
+    res = json.loads(line[-1])
+    for k in ("multicast", "unicast", "two_shot"):
+        if k + "_error" in res and "multicast" in res[k + "_error"].lower():
+            continue  # no NVSwitch multicast on this box
+        assert res.get(k + "_max_err", 1.0) <= 1e-5, res
