@@ -161,3 +161,51 @@ def test_peer_memory_exchange_matches_nccl_on_two_gpus():
         if k + "_error" in res and "multicast" in res[k + "_error"].lower():
             continue  # no NVSwitch multicast on this box
         assert res.get(k + "_max_err", 1.0) <= 1e-5, res
+
+
+# ---- sampler / densify synchronisation ---------------------------------------------------------------
+def _plumbing_worker(rank, world, port, out):
+    import types
+
+    from fateavatar_b200 import parallel
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    smp = parallel.FrameShardSampler(103, rank, world, seed=7)
+    epochs = []
+    for e in range(2):
+        smp.set_epoch(e)
+        epochs.append(list(smp))
+    model = types.SimpleNamespace(xyz_gradient_accum=torch.full((50, 1), float(rank + 1)), denom=torch.full((50, 1), 2.0))
+    parallel.allreduce_densify_stats(model)
+    g = parallel.synced_generator("cpu", seed=11, step=3000)
+    picks = torch.multinomial(model.xyz_gradient_accum.view(-1), 20, replacement=True, generator=g)
+    bary = torch.rand(20, 3, generator=g)
+    out.put((rank, epochs, model.xyz_gradient_accum.clone(), model.denom.clone(), picks, bary))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_frame_shard_sampler_and_synchronised_densify_world2():
+    world = 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_plumbing_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, ep0, a0, d0, picks0, bary0), (_, ep1, a1, d1, picks1, bary1) = res
+    for e in range(2):
+        assert len(ep0[e]) == len(ep1[e]) == 51                       # same number of steps on every rank
+        assert not set(ep0[e]) & set(ep1[e])                         # disjoint shards
+        assert len(set(ep0[e]) | set(ep1[e])) == 102                 # an epoch covers the video (minus the remainder)
+    assert ep0[0] != ep0[1]                                           # reshuffled every epoch
+    assert torch.equal(a0, torch.full((50, 1), 3.0)) and torch.equal(a0, a1) and torch.equal(d0, torch.full((50, 1), 4.0))
+    assert torch.equal(picks0, picks1) and torch.equal(bary0, bary1)  # every rank densifies the same splats
