@@ -46,8 +46,8 @@ class SymmetricBucket:
         self.out_local = torch.empty(self.n, dtype=torch.float32, device=self.device)
         mc_base = int(self.hdl.multicast_ptr)
         if algo is None:
-            # measured on B200 / NVLink 5 at 6.2 MB: N = 2: 23 us one-shot unicast, 31 us one-shot multicast;
-            # N = 8: 85 / 83 us one-shot (NCCL 58 us) -> the two-shot algorithm takes over from 4 ranks
+            # measured on B200 / NVLink 5 at 6.2 MB: N = 2: 22 us one-shot unicast, 31 us one-shot multicast, 37 us
+            # two-shot; N = 8: 84 / 83 us one-shot, 33 us two-shot (NCCL: 39 / 58 us) -> two-shot from 4 ranks
             algo = os.environ.get("FATESPLAT_P2P_ALGO", "auto")
             if algo == "auto":
                 algo = "two_shot" if (self.world >= 4 and mc_base) else "one_shot"
