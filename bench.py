@@ -233,7 +233,7 @@ def main():
     import numpy as np
     import torch
 
-    from fateavatar_b200 import _lib, rasterizer as R, render as rmod, scenes
+    from fateavatar_b200 import _lib, rasterizer as R, scenes
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl new needs a CUDA device (no CPU fallback exists)")

@@ -3,7 +3,7 @@
 plain torch ops (two lbs() calls per frame, as model/fateavatar.py:211-222 does)."""
 import os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
-import numpy as np, torch
+import torch
 from fateavatar_b200 import _lib, flame, scenes
 from oracle import flame_oracle as fo
 dev = torch.device("cuda:0")

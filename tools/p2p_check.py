@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """torchrun check of the peer-memory exchange: fs_p2p_allreduce (multicast and unicast) vs NCCL all_reduce, and timing.
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/p2p_check.py"""
-import json, os, sys, time
+import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch, torch.distributed as dist
 from fateavatar_b200.exchange import SymmetricBucket

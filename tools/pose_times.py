@@ -2,7 +2,7 @@
 """Fused pose kernel vs the same computation as plain torch ops (the reference's formulation) on the GPU."""
 import os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
-import numpy as np, torch
+import torch
 from fateavatar_b200 import pose, scenes
 from oracle import pose_oracle as po
 dev = torch.device("cuda:0")
