@@ -40,11 +40,15 @@ void fs_set_error(const char* fmt, ...) {
 }
 void fs_count_launch(int n) { g_launches += n; }
 
+#include <atomic>
 #include <cstdlib>
 #include <map>
+#include <mutex>
 #include <string>
 int fs_tuning(const char* env_name, int default_value) {
     static std::map<std::string, int> cache;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(env_name);
     if (it != cache.end()) return it->second;
     const char* v = getenv(env_name);
@@ -86,14 +90,23 @@ FsStageTimer::~FsStageTimer() {
     if (slot >= 0) cudaEventRecord(g_prof[slot].stop, stream);
 }
 
-int fs_num_sms() {
-    static int n = 0;
+int fs_num_sms() {  // per device: a process may drive more than one GPU
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int n = cache[dev & 63].load(std::memory_order_relaxed);
     if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cache[dev & 63].store(n, std::memory_order_relaxed);
     }
     return n;
+}
+
+bool fs_first_use_on_device(std::atomic<unsigned long long>& mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    return (mask.fetch_or(bit) & bit) == 0;
 }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

@@ -538,11 +538,9 @@ void fs_launch_backward(int P, int D, int M, const float* bg, int W, int H, cons
     {
         FsStageTimer timer(FS_STAGE_BLEND_BWD, stream);
         const size_t smem = sizeof(WarpStage) * kWarps + sizeof(uint64_t) * 2 * kWarps;
-        static bool attr_set = false;
-        if (!attr_set) {
+        static std::atomic<unsigned long long> attr_set{0};
+        if (fs_first_use_on_device(attr_set))
             cudaFuncSetAttribute(blend_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr_set = true;
-        }
         auto* info = reinterpret_cast<fs_frame_info*>(ws + L.info);
         const int ctas_per_sm = fs_tuning("FATESPLAT_BWD_CTAS_PER_SM", 2);  // upper bound (100 regs/thread)
         const int grid = fs_num_sms() * ctas_per_sm;

@@ -468,11 +468,9 @@ void fs_launch_binning(int P, int W, int H, char* ws, const fs_workspace_layout&
         fs_count_launch(3);
         return;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<unsigned long long> attr_set{0};
+    if (fs_first_use_on_device(attr_set))
         cudaFuncSetAttribute(big_tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBigSmemBytes);
-        attr_set = true;
-    }
     {
         FsStageTimer t(FS_STAGE_BIG_TILE_SORT, stream);
         fs_launch_pdl(big_tile_sort_kernel, dim3(64), dim3(kBigThreads), kBigSmemBytes, stream, big, ranges, keys, splat,

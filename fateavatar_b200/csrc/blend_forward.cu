@@ -235,11 +235,9 @@ void fs_launch_blend_forward(int W, int H, const float* bg, float* out_color, ch
     const int gx = (W + FS_TILE - 1) / FS_TILE, gy = (H + FS_TILE - 1) / FS_TILE;
     FsStageTimer timer(FS_STAGE_BLEND_FWD, stream);
     const size_t smem = sizeof(WarpStage) * kWarps + sizeof(uint64_t) * kStages * kWarps;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<unsigned long long> attr_set{0};
+    if (fs_first_use_on_device(attr_set))
         cudaFuncSetAttribute(blend_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
     auto* info = reinterpret_cast<fs_frame_info*>(ws + L.info);
     const int ctas_per_sm = fs_tuning("FATESPLAT_FWD_CTAS_PER_SM", 4);  // upper bound; see the kernel prologue
     const int grid = fs_num_sms() * ctas_per_sm;

