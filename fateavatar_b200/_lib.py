@@ -110,6 +110,43 @@ def load():
     return lib
 
 
+def stream_ptr(dev):
+    """Raw cudaStream_t of torch's current stream on `dev` (what every launch in this package goes to).  The
+    private accessor is ~30x cheaper than torch.cuda.current_stream(dev).cuda_stream, which matters when a frame is
+    a dozen ctypes calls."""
+    import torch
+
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    return torch._C._cuda_getCurrentRawStream(idx)
+
+
+class on_device:
+    """`with on_device(dev):` -- make `dev` the current CUDA device for the launches inside; free when it already is."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, dev):
+        self.idx = dev.index if dev.index is not None else -1
+        self.prev = -1
+
+    def __enter__(self):
+        import torch
+
+        if self.idx >= 0:
+            cur = torch.cuda.current_device()
+            if cur != self.idx:
+                self.prev = cur
+                torch.cuda.set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev >= 0:
+            import torch
+
+            torch.cuda.set_device(self.prev)
+            self.prev = -1
+        return False
+
+
 def check(rc, what):
     if rc != FS_OK:
         raise FateSplatError(f"{what} failed ({rc}): {load().fs_last_error().decode()}")

@@ -30,10 +30,10 @@ def densify_stats_raw(xyz_gradient_accum, denom, viewspace_grad, update_filter):
     if xyz_gradient_accum.numel() != P or denom.numel() != P or update_filter.numel() != P or viewspace_grad.shape[1] != 3:
         raise FateSplatError("densify_stats: shape mismatch")
     dev = viewspace_grad.device
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         rc = _lib.load().fs_densify_stats(P, viewspace_grad.data_ptr(), update_filter.data_ptr(),
                                           xyz_gradient_accum.data_ptr(), denom.data_ptr(),
-                                          torch.cuda.current_stream(dev).cuda_stream)
+                                          _lib.stream_ptr(dev))
     _lib.check(rc, "fs_densify_stats")
 
 

@@ -73,8 +73,8 @@ class SymmetricBucket:
         stream."""
         n = self.n if n is None else (int(n) + 3) // 4 * 4
         lib = _lib.load()
-        with torch.cuda.device(self.device):
-            stream = torch.cuda.current_stream(self.device).cuda_stream
+        with _lib.on_device(self.device):
+            stream = _lib.stream_ptr(self.device)
             self.hdl.barrier(channel=0)  # every rank's bucket of this step is complete and visible
             if self.algo == "two_shot":
                 rc = lib.fs_p2p_reduce_scatter_bcast(self.world, self.rank, self.multicast_base + 4 * (step & 1) * self.n,

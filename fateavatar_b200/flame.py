@@ -44,12 +44,12 @@ def flame_forward_raw(betas, pose, v_template, shapedirs, posedirs, J_regressor,
     if out is not None:
         verts, verts_orig, pf, A, A_orig, ws = (out[k] for k in ("verts", "verts_orig", "pose_feature", "transforms",
                                                                  "transforms_orig", "workspace"))
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             rc = lib.fs_flame_forward(V, L, int(l0), J, pc, betas.data_ptr(), pose.data_ptr(), v_template.data_ptr(),
                                       _ptr(delta_vertex), shapedirs.data_ptr(), _ptr(delta_shapedirs), posedirs.data_ptr(),
                                       _ptr(delta_posedirs), J_regressor.data_ptr(), lbs_weights.data_ptr(),
                                       verts.data_ptr(), _ptr(verts_orig), pf.data_ptr(), A.data_ptr(), _ptr(A_orig),
-                                      ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream)
+                                      ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
         _lib.check(rc, "fs_flame_forward")
         return out
     ws = workspace if workspace is not None and workspace.numel() >= nbytes else torch.empty(nbytes, dtype=torch.uint8, device=dev)
@@ -58,12 +58,12 @@ def flame_forward_raw(betas, pose, v_template, shapedirs, posedirs, J_regressor,
     pf = torch.empty(((J - 1) * 9,), device=dev)
     A = torch.empty((J, 4, 4), device=dev)
     A_orig = torch.empty((J, 4, 4), device=dev) if want_orig else None
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         rc = lib.fs_flame_forward(V, L, int(l0), J, pc, betas.data_ptr(), pose.data_ptr(), v_template.data_ptr(),
                                   _ptr(delta_vertex), shapedirs.data_ptr(), _ptr(delta_shapedirs), posedirs.data_ptr(),
                                   _ptr(delta_posedirs), J_regressor.data_ptr(), lbs_weights.data_ptr(), verts.data_ptr(),
                                   _ptr(verts_orig), pf.data_ptr(), A.data_ptr(), _ptr(A_orig), ws.data_ptr(), ws.numel(),
-                                  torch.cuda.current_stream(dev).cuda_stream)
+                                  _lib.stream_ptr(dev))
     _lib.check(rc, "fs_flame_forward")
     return dict(verts=verts, verts_orig=verts_orig, pose_feature=pf, transforms=A, transforms_orig=A_orig, workspace=ws)
 
@@ -97,12 +97,12 @@ def flame_backward_raw(betas, J_regressor, parents, lbs_weights, workspace, dL_d
     else:
         gs = torch.empty((V, 3), device=dev) if factors else None
         gp = torch.empty((V, 3), device=dev) if factors else None
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         rc = lib.fs_flame_backward(V, L, int(l0), J, pc, betas.data_ptr(), J_regressor.data_ptr(), lbs_weights.data_ptr(),
                                    dL_dverts.data_ptr(), workspace.data_ptr(), workspace.numel(),
                                    _ptr(o[0]) if want[0] else None, _ptr(o[1]) if want[1] else None,
                                    _ptr(o[2]) if want[2] else None, _ptr(gs), _ptr(gp), _ptr(header),
-                                   torch.cuda.current_stream(dev).cuda_stream)
+                                   _lib.stream_ptr(dev))
     _lib.check(rc, "fs_flame_backward")
     return (o[0], o[1], o[2]) + ((gs, gp) if factors else ())
 
@@ -229,10 +229,10 @@ def expand_factors(gathered, V, L, NP, l0=0, scale=1.0, out=None):
     N, stride = gathered.shape
     o = list(out) if out is not None else [torch.empty((V, 3), device=dev), torch.empty((V, 3, L), device=dev),
                                             torch.empty((NP, 3 * V), device=dev)]
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         rc = _lib.load().fs_flame_expand_grads(N, V, L, int(l0), NP, gathered.data_ptr(), stride, float(scale),
                                                _ptr(o[0]), _ptr(o[1]), _ptr(o[2]),
-                                               torch.cuda.current_stream(dev).cuda_stream)
+                                               _lib.stream_ptr(dev))
     _lib.check(rc, "fs_flame_expand_grads")
     return tuple(o)
 

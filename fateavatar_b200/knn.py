@@ -20,8 +20,8 @@ def distCUDA2(points: torch.Tensor) -> torch.Tensor:
         return means
     nbytes = lib.fs_knn_workspace_bytes(P)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=pts.device)
-    with torch.cuda.device(pts.device):
+    with _lib.on_device(pts.device):
         rc = lib.fs_knn_mean_dist2(P, pts.data_ptr(), means.data_ptr(), ws.data_ptr(), nbytes,
-                                   torch.cuda.current_stream(pts.device).cuda_stream)
+                                   _lib.stream_ptr(pts.device))
         _lib.check(rc, "fs_knn_mean_dist2")
     return means

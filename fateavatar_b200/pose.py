@@ -35,7 +35,7 @@ def pose_forward_raw(verts, faces, face_index, bary, canon, scaling_raw, rotatio
                              canon.data_ptr(), scaling_raw.data_ptr(), rotation_raw.data_ptr(), offset_raw.data_ptr(),
                              opacity_raw.data_ptr(), float(shell_len), int(bool(resize_scale)), xyz.data_ptr(),
                              scales.data_ptr(), rots.data_ptr(), opac.data_ptr(),
-                             torch.cuda.current_stream(dev).cuda_stream)
+                             _lib.stream_ptr(dev))
     _lib.check(rc, "fs_pose_forward")
     return xyz, scales, rots, opac
 
@@ -54,7 +54,7 @@ def pose_backward_raw(verts, faces, face_index, bary, canon, scaling_raw, rotati
                               opacity_raw.data_ptr(), float(shell_len), int(bool(resize_scale)), g_xyz.data_ptr(),
                               g_scales.data_ptr(), g_rots.data_ptr(), g_opac.data_ptr(), d_verts.data_ptr(),
                               d_sr.data_ptr(), d_rr.data_ptr(), d_of.data_ptr(), d_op.data_ptr(),
-                              torch.cuda.current_stream(dev).cuda_stream)
+                              _lib.stream_ptr(dev))
     _lib.check(rc, "fs_pose_backward")
     return d_verts, d_sr, d_rr, d_of, d_op
 
@@ -77,11 +77,11 @@ class _PoseSplats(torch.autograd.Function):
         scales = torch.empty((N, 3), device=dev)
         rots = torch.empty((N, 4), device=dev)
         opac = torch.empty((N, 1), device=dev)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             rc = lib.fs_pose_forward(N, V, F, v.data_ptr(), fc.data_ptr(), fi.data_ptr(), bc.data_ptr(), cn.data_ptr(),
                                      sr.data_ptr(), rr.data_ptr(), of.data_ptr(), opr.data_ptr(), float(shell_len),
                                      int(bool(resize_scale)), xyz.data_ptr(), scales.data_ptr(), rots.data_ptr(),
-                                     opac.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+                                     opac.data_ptr(), _lib.stream_ptr(dev))
         _lib.check(rc, "fs_pose_forward")
         ctx.save_for_backward(v, sr, rr, of, opr, fc, fi, bc, cn)
         ctx.meta = (float(shell_len), int(bool(resize_scale)), verts.shape)
@@ -99,12 +99,12 @@ class _PoseSplats(torch.autograd.Function):
         d_verts = torch.empty((V, 3), device=dev)  # zero-filled by the library
         d_sr, d_rr = torch.empty_like(sr), torch.empty_like(rr)
         d_of, d_op = torch.empty_like(of), torch.empty_like(opr)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             rc = lib.fs_pose_backward(N, V, F, v.data_ptr(), fc.data_ptr(), fi.data_ptr(), bc.data_ptr(), cn.data_ptr(),
                                       sr.data_ptr(), rr.data_ptr(), of.data_ptr(), opr.data_ptr(), shell_len, resize,
                                       g_xyz.data_ptr(), g_scales.data_ptr(), g_rots.data_ptr(), g_opac.data_ptr(),
                                       d_verts.data_ptr(), d_sr.data_ptr(), d_rr.data_ptr(), d_of.data_ptr(),
-                                      d_op.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+                                      d_op.data_ptr(), _lib.stream_ptr(dev))
         _lib.check(rc, "fs_pose_backward")
         return d_verts.reshape(vshape), d_sr, d_rr, d_of, d_op, None, None, None, None, None, None
 

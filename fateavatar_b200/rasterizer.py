@@ -119,14 +119,14 @@ def _drain_pending(ent, dev, block=False):
 _POISON = 0xFFFFFFFF
 
 
-def _wait_num_rendered(info, stream):
+def _wait_num_rendered(info, dev):
     """Synchronous mode: block until this frame's instance count is known, like the reference's blocking read of
     num_rendered (rasterizer_impl.cu:281) -- but only until the scan kernel has stored it into the pinned header
     (fs_forward's early notification), not until the frame has finished, so the host keeps the stream fed."""
     spins = 0
     while info.num_rendered == _POISON:
         spins += 1
-        if (spins & 255) == 0 and stream.query():  # nothing left on the stream: the header must have arrived
+        if (spins & 1023) == 0 and torch.cuda.current_stream(dev).query():  # stream drained: it must have arrived
             if info.num_rendered == _POISON:
                 raise FateSplatError("fs_forward finished without reporting num_rendered (pinned header not written)")
     return info
@@ -188,8 +188,8 @@ def forward_raw(raster_settings, means3D, sh, colors_precomp, opacities, scales,
         di = dev.index if dev.index is not None else torch.cuda.current_device()
         key = (di, W, H)
         ent = _pinned_slots(di)
-        with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev)
+        with _lib.on_device(dev):
+            stream_ptr = _lib.stream_ptr(dev)
             capturing = torch.cuda.is_current_stream_capturing()
             if _ASYNC and not capturing:
                 _drain_pending(ent, di)
@@ -211,7 +211,7 @@ def forward_raw(raster_settings, means3D, sh, colors_precomp, opacities, scales,
                                     _ptr(sc_c), float(rs.scale_modifier), _ptr(ro_c), _ptr(c3_c), _ptr(view),
                                     _ptr(proj), _ptr(campos), float(rs.tanfovx), float(rs.tanfovy),
                                     int(bool(rs.prefiltered)), color.data_ptr(), radii.data_ptr(),
-                                    workspace.data_ptr(), nbytes, capacity, header.data_ptr(), stream.cuda_stream)
+                                    workspace.data_ptr(), nbytes, capacity, header.data_ptr(), stream_ptr)
                 _lib.check(rc, "fs_forward")
                 launches += lib.fs_last_launch_count()
                 num_rendered = -1
@@ -230,16 +230,16 @@ def forward_raw(raster_settings, means3D, sh, colors_precomp, opacities, scales,
                                     _ptr(sc_c), float(rs.scale_modifier), _ptr(ro_c), _ptr(c3_c), _ptr(view),
                                     _ptr(proj), _ptr(campos), float(rs.tanfovx), float(rs.tanfovy),
                                     int(bool(rs.prefiltered)), color.data_ptr(), radii.data_ptr(),
-                                    workspace.data_ptr(), nbytes, capacity, h_info, stream.cuda_stream)
+                                    workspace.data_ptr(), nbytes, capacity, h_info, stream_ptr)
                 _lib.check(rc, "fs_forward")
                 launches += lib.fs_last_launch_count()
                 if _ASYNC:
                     ev = torch.cuda.Event()
-                    ev.record(stream)
+                    ev.record(torch.cuda.current_stream(dev))
                     ent["pending"].append((slot, ev, key))
                     num_rendered = -1
                     break
-                _wait_num_rendered(info, stream)
+                _wait_num_rendered(info, dev)
                 num_rendered = int(info.num_rendered)
                 _capacity_hint[key] = max(num_rendered, int(_capacity_hint.get(key, 0) * 0.9))
                 _tile_hint[key] = max(int(info.max_tile_instances), int(_tile_hint.get(key, 0) * 0.9))
@@ -292,8 +292,7 @@ def backward_raw(state, grad_out_color, out=None):
         if grad_out_color.dtype != torch.float32:
             grad_out_color = grad_out_color.float()
         dpix = grad_out_color.contiguous()
-        with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev)
+        with _lib.on_device(dev):
             if _ASYNC and not torch.cuda.is_current_stream_capturing():
                 di = dev.index if dev.index is not None else torch.cuda.current_device()
                 _drain_pending(_pinned_slots(di), di, block=True)  # the frame must not have overflowed
@@ -303,7 +302,7 @@ def backward_raw(state, grad_out_color, out=None):
                                  workspace.data_ptr(), workspace.numel(), state["capacity"], dpix.data_ptr(),
                                  g_means2D.data_ptr(), g_opacity.data_ptr(), g_colors.data_ptr(),
                                  g_means3D.data_ptr(), g_cov3D.data_ptr(), _ptr(g_sh), g_scales.data_ptr(),
-                                 g_rot.data_ptr(), stream.cuda_stream)
+                                 g_rot.data_ptr(), _lib.stream_ptr(dev))
             _lib.check(rc, "fs_backward")
             state["launches_bwd"] = lib.fs_last_launch_count()
         if rs.debug:
@@ -358,10 +357,10 @@ class GaussianRasterizer(nn.Module):
             P = pos.shape[0]
             present = torch.zeros((P,), dtype=torch.uint8, device=pos.device)
             if P:
-                with torch.cuda.device(pos.device):
+                with _lib.on_device(pos.device):
                     rc = _lib.load().fs_mark_visible(P, pos.data_ptr(), rs.viewmatrix.contiguous().data_ptr(),
                                                      rs.projmatrix.contiguous().data_ptr(), present.data_ptr(),
-                                                     torch.cuda.current_stream(pos.device).cuda_stream)
+                                                     _lib.stream_ptr(pos.device))
                     _lib.check(rc, "fs_mark_visible")
             return present.bool()
 
