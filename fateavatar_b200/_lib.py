@@ -38,7 +38,7 @@ EXPORTS = [
     "fs_workspace_bytes", "fs_get_workspace_layout", "fs_forward", "fs_backward", "fs_mark_visible",
     "fs_knn_workspace_bytes", "fs_knn_mean_dist2", "fs_last_launch_count", "fs_last_error", "fs_version",
     "fs_profile_enable", "fs_profile_read", "fs_pose_forward", "fs_pose_backward", "fs_set_tile_hint",
-    "fs_flame_workspace_bytes", "fs_flame_forward", "fs_flame_backward", "fs_densify_stats", "fs_flame_expand_grads", "fs_p2p_allreduce", "fs_p2p_reduce_scatter_bcast",
+    "fs_flame_workspace_bytes", "fs_flame_forward", "fs_flame_backward", "fs_flame_backward_coeffs", "fs_densify_stats", "fs_flame_expand_grads", "fs_p2p_allreduce", "fs_p2p_reduce_scatter_bcast",
 ]
 
 STAGES = ["preprocess", "tile_scan", "scatter", "tile_sort", "big_tile_sort", "blend_forward", "blend_backward",
@@ -89,6 +89,8 @@ def load():
     lib.fs_flame_forward.argtypes = [i, i, i, i, C.POINTER(C.c_int)] + [vp] * 10 + [vp] * 5 + [vp, sz, vp]
     lib.fs_flame_backward.restype = i
     lib.fs_flame_backward.argtypes = [i, i, i, i, C.POINTER(C.c_int)] + [vp] * 4 + [vp, sz] + [vp] * 6 + [vp]
+    lib.fs_flame_backward_coeffs.restype = i
+    lib.fs_flame_backward_coeffs.argtypes = [i, i, i, i, C.POINTER(C.c_int)] + [vp] * 6 + [vp, sz, vp, vp, vp]
     lib.fs_flame_expand_grads.restype = i
     lib.fs_flame_expand_grads.argtypes = [i, i, i, i, i, vp, sz, f, vp, vp, vp, vp]
     lib.fs_p2p_reduce_scatter_bcast.restype = i

@@ -50,7 +50,7 @@ struct FlameState {
 };
 
 struct FlameWs {  // byte offsets inside the workspace
-    size_t state, v_shaped, v_posed, g_posed, jpart, dapart, total;
+    size_t state, v_shaped, v_posed, g_posed, jpart, dapart, bpart, pfpart, drloc, total;
     int nblk_blend, nblk_skin;
 };
 
@@ -72,6 +72,12 @@ FlameWs flame_layout(int V) {
     o = al(o + (size_t)w.nblk_blend * 2 * kMaxJ * 3 * sizeof(float));
     w.dapart = o;
     o = al(o + (size_t)w.nblk_skin * kMaxJ * 12 * sizeof(float));
+    w.bpart = o;  // coefficient-gradient partials (fs_flame_backward_coeffs): [128 columns][#SM CTAs]
+    o = al(o + (size_t)fs_num_sms() * 128 * sizeof(float));
+    w.pfpart = o;
+    o = al(o + (size_t)8 * 64 * sizeof(float));
+    w.drloc = o;
+    o = al(o + (size_t)kMaxJ * 9 * sizeof(float));
     w.total = o;
     return w;
 }
@@ -340,7 +346,8 @@ flame_skin_kernel(int V, int J, Parents parents, int nblk_blend, const float* __
 __global__ void __launch_bounds__(kSkinBwdThreads)
 flame_skin_backward_kernel(int V, int J, const float* __restrict__ lbs_weights, const FlameState* __restrict__ state,
                            const float* __restrict__ v_posed, const float* __restrict__ dL_dverts,
-                           float* __restrict__ g_posed, float* __restrict__ dapart /*[12J][grid]*/) {
+                           float* __restrict__ g_posed, float* __restrict__ g_posed_user,
+                           float* __restrict__ dapart /*[12J][grid]*/) {
     __shared__ float s_A[kMaxJ][12];
     __shared__ float s_g[kSkinBwdThreads], s_vp[kSkinBwdThreads], s_w[kSkinVerts][kMaxJ];
     const int t = threadIdx.x;
@@ -364,6 +371,7 @@ flame_skin_backward_kernel(int V, int J, const float* __restrict__ lbs_weights, 
             acc += T * s_g[3 * vl + k];
         }
         g_posed[e] = acc;
+        if (g_posed_user) g_posed_user[e] = acc;
     }
     if (t < J * 12) {  // dL/dA[j][k][c] = sum_v W[v][j] g[v][k] (c < 3 ? v_posed[v][c] : 1), this CTA's vertices
         const int j = t / 12, k = (t % 12) / 4, c = t % 4;
@@ -373,6 +381,53 @@ flame_skin_backward_kernel(int V, int J, const float* __restrict__ lbs_weights, 
         dapart[(size_t)t * gridDim.x + blockIdx.x] = acc;  // [slot][CTA]
     }
     fs::pdl_trigger();
+}
+
+// Backward of the kinematic chain (lbs.py:285-342) on one warp, everything in shared memory.
+//   A[j] = [Rg_j | tg_j - Rg_j J_j];  Rg_j = Rg_p R_j;  tg_j = Rg_p (J_j - J_p) + tg_p  (j > 0);  tg_0 = J_0
+// in : dA (sum over vertices of W g (x) [v_posed; 1]);  out: dJ (joints) and, when dRloc != nullptr, the gradient of
+// every joint's LOCAL rotation R_j (the path to the pose coefficients).  Lanes 0..8 own the entries of dRg, 9..11
+// those of drel / dJ, 12..14 those of dtg, 16..24 those of dRloc.
+__device__ __forceinline__ void chain_backward_warp(int lane, int J, const Parents& parents, const FlameState& S,
+                                                    float (*s_dA)[12], float (*s_dRg)[9], float (*s_dtg)[3],
+                                                    float (*s_dJ)[3], float (*s_dRloc)[9]) {
+    for (int i = lane; i < J * 12; i += 32) {
+        const int j = i / 12, r = i % 12;
+        if (r < 9) s_dRg[j][r] = s_dA[j][(r / 3) * 4 + r % 3] - s_dA[j][(r / 3) * 4 + 3] * S.J[0][j][r % 3];
+        else s_dtg[j][r - 9] = s_dA[j][(r - 9) * 4 + 3];
+    }
+    __syncwarp();
+    for (int i = lane; i < J * 3; i += 32) {
+        const int j = i / 3, b = i % 3;
+        const float* G = S.Rg[0][j];
+        s_dJ[j][b] = -(G[b] * s_dtg[j][0] + G[3 + b] * s_dtg[j][1] + G[6 + b] * s_dtg[j][2]);
+    }
+    __syncwarp();
+    for (int j = J - 1; j >= 1; --j) {
+        const int pa = parents.p[j];
+        if (lane < 9) {  // dRg_p += dRg_j R_j^T + dtg_j (x) rel
+            const int a = lane / 3, b = lane % 3;
+            const float* Rj = S.R[j];
+            const float rel = S.J[0][j][b] - S.J[0][pa][b];
+            s_dRg[pa][lane] += s_dRg[j][a * 3] * Rj[b * 3] + s_dRg[j][a * 3 + 1] * Rj[b * 3 + 1] +
+                               s_dRg[j][a * 3 + 2] * Rj[b * 3 + 2] + s_dtg[j][a] * rel;
+        } else if (lane < 12) {  // drel = Rg_p^T dtg_j
+            const int b = lane - 9;
+            const float* Gp = S.Rg[0][pa];
+            const float drel = Gp[b] * s_dtg[j][0] + Gp[3 + b] * s_dtg[j][1] + Gp[6 + b] * s_dtg[j][2];
+            s_dJ[j][b] += drel;
+            s_dJ[pa][b] -= drel;
+        } else if (s_dRloc && lane >= 16 && lane < 25) {  // dR_j = Rg_p^T dRg_j (dRg_j is final: children came first)
+            const int a = (lane - 16) / 3, b = (lane - 16) % 3;
+            const float* Gp = S.Rg[0][pa];
+            s_dRloc[j][lane - 16] = Gp[a] * s_dRg[j][b] + Gp[3 + a] * s_dRg[j][3 + b] + Gp[6 + a] * s_dRg[j][6 + b];
+        }
+        __syncwarp();
+        if (lane >= 12 && lane < 15) s_dtg[pa][lane - 12] += s_dtg[j][lane - 12];
+        __syncwarp();
+    }
+    if (lane < 3) s_dJ[0][lane] += s_dtg[0][lane];
+    if (s_dRloc && lane < 9) s_dRloc[0][lane] = s_dRg[0][lane];
 }
 
 // ---- backward 2: chain backward + parameter gradients -------------------------------------------------------
@@ -398,42 +453,7 @@ flame_blend_backward_kernel(int V, int L, int l0, int J, Parents parents, int nb
         if (live && (t & 7) == 0) s_dA[slot / 12][slot % 12] = sum;
     }
     __syncthreads();
-    if (wid == 0) {
-        // A[j] = [Rg_j | tg_j - Rg_j J_j];  Rg_j = Rg_p R_j;  tg_j = Rg_p (J_j - J_p) + tg_p  (j > 0);  tg_0 = J_0
-        // lanes 0..8 own the entries of dRg, 9..11 those of drel / dJ, 12..14 those of dtg
-        for (int i = lane; i < J * 12; i += 32) {
-            const int j = i / 12, r = i % 12;
-            if (r < 9) s_dRg[j][r] = s_dA[j][(r / 3) * 4 + r % 3] - s_dA[j][(r / 3) * 4 + 3] * S.J[0][j][r % 3];
-            else s_dtg[j][r - 9] = s_dA[j][(r - 9) * 4 + 3];
-        }
-        __syncwarp();
-        for (int i = lane; i < J * 3; i += 32) {
-            const int j = i / 3, b = i % 3;
-            const float* G = S.Rg[0][j];
-            s_dJ[j][b] = -(G[b] * s_dtg[j][0] + G[3 + b] * s_dtg[j][1] + G[6 + b] * s_dtg[j][2]);
-        }
-        __syncwarp();
-        for (int j = J - 1; j >= 1; --j) {
-            const int pa = parents.p[j];
-            if (lane < 9) {  // dRg_p += dRg_j R_j^T + dtg_j (x) rel
-                const int a = lane / 3, b = lane % 3;
-                const float* Rj = S.R[j];
-                const float rel = S.J[0][j][b] - S.J[0][pa][b];
-                s_dRg[pa][lane] += s_dRg[j][a * 3] * Rj[b * 3] + s_dRg[j][a * 3 + 1] * Rj[b * 3 + 1] +
-                                   s_dRg[j][a * 3 + 2] * Rj[b * 3 + 2] + s_dtg[j][a] * rel;
-            } else if (lane < 12) {  // drel = Rg_p^T dtg_j
-                const int b = lane - 9;
-                const float* Gp = S.Rg[0][pa];
-                const float drel = Gp[b] * s_dtg[j][0] + Gp[3 + b] * s_dtg[j][1] + Gp[6 + b] * s_dtg[j][2];
-                s_dJ[j][b] += drel;
-                s_dJ[pa][b] -= drel;
-            }
-            __syncwarp();
-            if (lane >= 12 && lane < 15) s_dtg[pa][lane - 12] += s_dtg[j][lane - 12];
-            __syncwarp();
-        }
-        if (lane < 3) s_dJ[0][lane] += s_dtg[0][lane];
-    }
+    if (wid == 0) chain_backward_warp(lane, J, parents, S, s_dA, s_dRg, s_dtg, s_dJ, nullptr);
     __syncthreads();
 
     if (factor_header && blockIdx.x == 0) {  // [betas | pose_feature]: the head of this rank's factor record
@@ -561,6 +581,152 @@ flame_expand_kernel(int N, int V, int L, int l0, int NP, const float* __restrict
     }
 }
 
+// ---- backward 3 (optional): gradients of the expression / pose COEFFICIENTS ---------------------------------------
+// Needed only when the caller optimises per-frame tracking (train/base.py:113-151); FateAvatar's INSTA runs do not.
+//   dL/dbetas[l] = sum_{v,k} dL/dv_shaped[v,k] (S + dS)[v,k,l]
+//   dL/dpose     = Rodrigues^T ( chain path: Rg_p^T dRg_j   +   pose-feature path: (P + dP) dL/dv_posed )
+// One chunk of <= 128 coefficients per launch: per-CTA partial sums in the workspace, fixed-order final reduction.
+constexpr int kCoeffChunk = 128, kCoeffThreads = 512, kPfSegs = 8;
+
+__global__ void __launch_bounds__(kCoeffThreads)
+flame_coeff_partial_kernel(int V, int L, int J, Parents parents, int nblk_skin, int c0, int nc, int do_pose,
+                           const float* __restrict__ shapedirs, const float* __restrict__ delta_shapedirs,
+                           const float* __restrict__ posedirs, const float* __restrict__ delta_posedirs,
+                           const float* __restrict__ J_regressor, const FlameState* __restrict__ state,
+                           const float* __restrict__ g_posed, const float* __restrict__ dapart,
+                           float* __restrict__ bpart /*[grid][128]*/, float* __restrict__ pfpart /*[kPfSegs][64]*/,
+                           float* __restrict__ drloc_out /*[kMaxJ][9]*/) {
+    __shared__ float s_dA[kMaxJ][12];
+    __shared__ float s_dJ[kMaxJ][3], s_dRg[kMaxJ][9], s_dtg[kMaxJ][3], s_dRloc[kMaxJ][9];
+    __shared__ FlameState S;
+    __shared__ float s_part[kCoeffThreads / 32][kCoeffChunk];
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int NP = (J - 1) * 9, n3 = 3 * V;
+    for (int i = t; i < (int)(sizeof(FlameState) / sizeof(float)); i += kCoeffThreads)
+        reinterpret_cast<float*>(&S)[i] = reinterpret_cast<const float*>(state)[i];
+    for (int base = 0; base < J * 12; base += kCoeffThreads / 8) {
+        const int slot = base + (t >> 3);
+        const bool live = slot < J * 12;
+        const float sum = reduce_partials8(dapart, live ? slot : 0, live ? nblk_skin : 0, nblk_skin, t & 7);
+        if (live && (t & 7) == 0) s_dA[slot / 12][slot % 12] = sum;
+    }
+    __syncthreads();
+    if (wid == 0) chain_backward_warp(lane, J, parents, S, s_dA, s_dRg, s_dtg, s_dJ, s_dRloc);
+    __syncthreads();
+    if (blockIdx.x == 0 && do_pose)
+        for (int i = t; i < J * 9; i += kCoeffThreads) drloc_out[i] = s_dRloc[i / 9][i % 9];
+
+    // this chunk of dL/dbetas: a warp per vertex, lane q-th column = c0 + lane + 32 q
+    float acc[kCoeffChunk / 32] = {0.f, 0.f, 0.f, 0.f};
+    const int nw = gridDim.x * (kCoeffThreads / 32);
+    for (int v = blockIdx.x * (kCoeffThreads / 32) + wid; v < V; v += nw) {
+        float gsk = 0.f;
+        if (lane < 3) {
+            gsk = g_posed[3 * v + lane];
+            for (int j = 0; j < J; ++j) gsk += __ldg(J_regressor + (size_t)j * V + v) * s_dJ[j][lane];
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float g = __shfl_sync(0xffffffffu, gsk, k);
+            const size_t row = ((size_t)v * 3 + k) * L + c0;
+#pragma unroll
+            for (int q = 0; q < kCoeffChunk / 32; ++q) {
+                const int col = lane + 32 * q;
+                if (col < nc) {
+                    float sv = __ldg(shapedirs + row + col);
+                    if (delta_shapedirs) sv += __ldg(delta_shapedirs + row + col);
+                    acc[q] += g * sv;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kCoeffChunk / 32; ++q) s_part[wid][lane + 32 * q] = acc[q];
+    __syncthreads();
+    if (t < kCoeffChunk) {
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < kCoeffThreads / 32; ++w) sum += s_part[w][t];
+        bpart[(size_t)t * gridDim.x + blockIdx.x] = sum;  // [column][CTA]
+    }
+    // pose-feature path: dpf[i] = sum_e (P + dP)[i,e] dL/dv_posed[e], split into kPfSegs segments per row
+    if (do_pose) {
+        const int gw = blockIdx.x * (kCoeffThreads / 32) + wid;
+        for (int task = gw; task < NP * kPfSegs; task += nw) {
+            const int i = task / kPfSegs, seg = task % kPfSegs;
+            const int per = (n3 + kPfSegs - 1) / kPfSegs, e0 = seg * per, e1 = min(n3, e0 + per);
+            float sum = 0.f;
+            for (int e = e0 + lane; e < e1; e += 32) {
+                float p = __ldg(posedirs + (size_t)i * n3 + e);
+                if (delta_posedirs) p += __ldg(delta_posedirs + (size_t)i * n3 + e);
+                sum += p * g_posed[e];
+            }
+            sum = warp_sum(sum);
+            if (lane == 0) pfpart[seg * 64 + i] = sum;
+        }
+    }
+}
+
+// Rodrigues backward (lbs.py:253-270): R = I + sin(a) K(u) + (1 - cos a) K(u)^2, a = ||r + 1e-8||, u = r / a
+__device__ void rodrigues_backward(const float* r, const float* dR, float* dr) {
+    const float ex = r[0] + 1e-8f, ey = r[1] + 1e-8f, ez = r[2] + 1e-8f;
+    const float a = sqrtf(ex * ex + ey * ey + ez * ez);
+    const float u[3] = {r[0] / a, r[1] / a, r[2] / a};
+    const float s = sinf(a), c = cosf(a);
+    const float K[9] = {0.f, -u[2], u[1], u[2], 0.f, -u[0], -u[1], u[0], 0.f};
+    float K2[9], dK[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) K2[i * 3 + j] = K[i * 3] * K[j] + K[i * 3 + 1] * K[3 + j] + K[i * 3 + 2] * K[6 + j];
+    float dLds = 0.f, dLdm = 0.f;  // d/d sin, d/d (1 - cos)
+    for (int i = 0; i < 9; ++i) {
+        dLds += dR[i] * K[i];
+        dLdm += dR[i] * K2[i];
+    }
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {  // dK = s dR + (1 - c) (dR K^T + K^T dR)
+            float x = 0.f;
+            for (int k = 0; k < 3; ++k) x += dR[i * 3 + k] * K[j * 3 + k] + K[k * 3 + i] * dR[k * 3 + j];
+            dK[i * 3 + j] = s * dR[i * 3 + j] + (1.0f - c) * x;
+        }
+    const float du[3] = {dK[7] - dK[5], dK[2] - dK[6], dK[3] - dK[1]};
+    const float dLda = dLds * c + dLdm * s;
+    const float dur = du[0] * r[0] + du[1] * r[1] + du[2] * r[2];
+    const float k = (dLda - dur / (a * a)) / a;
+    dr[0] = du[0] / a + k * ex;
+    dr[1] = du[1] / a + k * ey;
+    dr[2] = du[2] / a + k * ez;
+}
+
+__global__ void __launch_bounds__(256)
+flame_coeff_final_kernel(int L, int l0, int J, int nblk, int c0, int nc, int do_pose, int first,
+                         const float* __restrict__ pose, const float* __restrict__ bpart,
+                         const float* __restrict__ pfpart, const float* __restrict__ drloc,
+                         float* __restrict__ d_betas, float* __restrict__ d_pose) {
+    const int t = threadIdx.x;
+    if (d_betas) {
+        if (first)
+            for (int l = t; l < l0; l += 256) d_betas[l] = 0.0f;  // coefficients declared constant-zero by the caller
+        for (int col = t; col < nc; col += 256) {
+            float sum = 0.f;
+            for (int b = 0; b < nblk; ++b) sum += bpart[(size_t)col * nblk + b];
+            d_betas[c0 + col] = sum;
+        }
+    }
+    if (do_pose && d_pose && t < J) {
+        float dR[9], r[3] = {pose[3 * t], pose[3 * t + 1], pose[3 * t + 2]}, dr[3];
+        for (int e = 0; e < 9; ++e) {
+            float x = drloc[t * 9 + e];
+            if (t > 0)
+                for (int seg = 0; seg < kPfSegs; ++seg) x += pfpart[seg * 64 + (t - 1) * 9 + e];
+            dR[e] = x;
+        }
+        rodrigues_backward(r, dR, dr);
+        d_pose[3 * t] = dr[0];
+        d_pose[3 * t + 1] = dr[1];
+        d_pose[3 * t + 2] = dr[2];
+    }
+}
+
 bool parents_ok(int J, const int* parents_host, Parents& P) {
     if (J < 1 || J > kMaxJ || !parents_host) return false;
     for (int j = 0; j < kMaxJ; ++j) P.p[j] = 0;
@@ -656,10 +822,11 @@ int fs_flame_backward(int V, int L, int l0, int J, const int* parents_host, cons
     char* ws = static_cast<char*>(d_workspace);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     FsStageTimer timer(FS_STAGE_FLAME_BWD, st);
-    float* g_posed = d_dL_dv_posed ? d_dL_dv_posed : reinterpret_cast<float*>(ws + w.g_posed);
+    float* g_posed = reinterpret_cast<float*>(ws + w.g_posed);  // kept for fs_flame_backward_coeffs
     flame_skin_backward_kernel<<<w.nblk_skin, kSkinBwdThreads, 0, st>>>(
         V, J, d_lbs_weights, reinterpret_cast<const FlameState*>(ws + w.state),
-        reinterpret_cast<const float*>(ws + w.v_posed), d_dL_dverts, g_posed, reinterpret_cast<float*>(ws + w.dapart));
+        reinterpret_cast<const float*>(ws + w.v_posed), d_dL_dverts, g_posed, d_dL_dv_posed,
+        reinterpret_cast<float*>(ws + w.dapart));
     // enough CTAs to stream the 4 L V 3-byte delta_shapedirs gradient at full rate, few enough that the
     // redundant prologue (partials reduce + chain backward) stays negligible
     const int grid = d_dL_ddelta_shapedirs ? 2 * fs_num_sms() : fs_num_sms() / 2 + 1;
@@ -670,6 +837,55 @@ int fs_flame_backward(int V, int L, int l0, int J, const int* parents_host, cons
     fs_count_launch(2);
     if (cudaGetLastError() != cudaSuccess) {
         fs_set_error("fs_flame_backward: launch failed");
+        return FS_ERR_CUDA;
+    }
+    return FS_OK;
+}
+
+int fs_flame_backward_coeffs(int V, int L, int l0, int J, const int* parents_host, const float* d_pose,
+                             const float* d_shapedirs, const float* d_delta_shapedirs, const float* d_posedirs,
+                             const float* d_delta_posedirs, const float* d_J_regressor, void* d_workspace,
+                             size_t workspace_bytes, float* d_dL_dbetas, float* d_dL_dpose, void* stream) {
+    Parents P;
+    if (V <= 0 || L <= 0 || l0 < 0 || l0 > L || !parents_ok(J, parents_host, P)) {
+        fs_set_error("fs_flame_backward_coeffs: invalid size or kinematic tree");
+        return FS_ERR_INVALID_ARGUMENT;
+    }
+    if (!d_pose || !d_shapedirs || !d_posedirs || !d_J_regressor || !d_workspace) {
+        fs_set_error("fs_flame_backward_coeffs: required pointer is NULL");
+        return FS_ERR_INVALID_ARGUMENT;
+    }
+    const FlameWs w = flame_layout(V);
+    if (workspace_bytes < w.total) {
+        fs_set_error("fs_flame_backward_coeffs: workspace too small (%zu < %zu bytes)", workspace_bytes, w.total);
+        return FS_ERR_WORKSPACE_TOO_SMALL;
+    }
+    if (!d_dL_dbetas && !d_dL_dpose) return FS_OK;
+    char* ws = static_cast<char*>(d_workspace);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FsStageTimer timer(FS_STAGE_FLAME_BWD, st);
+    const int grid = fs_num_sms();
+    const int n = d_dL_dbetas ? L - l0 : 0;
+    int launches = 0;
+    for (int c0 = l0, first = 1; first || c0 < l0 + n; c0 += kCoeffChunk, first = 0) {
+        const int nc = std::max(0, std::min(kCoeffChunk, l0 + n - c0));
+        const int do_pose = first && d_dL_dpose;
+        flame_coeff_partial_kernel<<<grid, kCoeffThreads, 0, st>>>(
+            V, L, J, P, w.nblk_skin, c0, nc, do_pose, d_shapedirs, d_delta_shapedirs, d_posedirs, d_delta_posedirs,
+            d_J_regressor, reinterpret_cast<const FlameState*>(ws + w.state),
+            reinterpret_cast<const float*>(ws + w.g_posed), reinterpret_cast<const float*>(ws + w.dapart),
+            reinterpret_cast<float*>(ws + w.bpart), reinterpret_cast<float*>(ws + w.pfpart),
+            reinterpret_cast<float*>(ws + w.drloc));
+        flame_coeff_final_kernel<<<1, 256, 0, st>>>(L, l0, J, grid, c0, nc, do_pose, first, d_pose,
+                                                    reinterpret_cast<const float*>(ws + w.bpart),
+                                                    reinterpret_cast<const float*>(ws + w.pfpart),
+                                                    reinterpret_cast<const float*>(ws + w.drloc), d_dL_dbetas,
+                                                    d_dL_dpose);
+        launches += 2;
+    }
+    fs_count_launch(launches);
+    if (cudaGetLastError() != cudaSuccess) {
+        fs_set_error("fs_flame_backward_coeffs: launch failed");
         return FS_ERR_CUDA;
     }
     return FS_OK;

@@ -9,8 +9,8 @@ Mirrors flame/FLAME.py:131-204 (`FLAME.forward`, `FLAME.forward_with_delta_blend
 FateAvatar calls both, back to back, every frame (model/fateavatar.py:211-222).  `fs_flame_forward` produces both
 results in one pass over the blendshape tensors; `attach(flame_module)` rebinds the two methods of an existing
 reference FLAME module so the caller runs unchanged (the second call is served from the first one's by-product).
-Gradients flow to delta_shapedirs / delta_posedirs / delta_vertex (the parameters FateAvatar trains); expression
-and pose are dataset inputs upstream -- asking for their gradient raises instead of silently returning None.
+Gradients flow to delta_shapedirs / delta_posedirs / delta_vertex (the parameters FateAvatar trains) and, when they
+require grad (per-frame tracking optimisation, train/base.py:113-151), to the expression and pose coefficients.
 CUDA only; no CPU path.
 """
 import ctypes as C
@@ -112,15 +112,14 @@ class _FlameLBS(torch.autograd.Function):
     def forward(ctx, betas, pose, delta_vertex, delta_shapedirs, delta_posedirs, model, l0, want_orig):
         if not model["v_template"].is_cuda:
             raise FateSplatError("flame_lbs needs CUDA tensors: fateavatar_b200 has no CPU path")
-        if betas.requires_grad or pose.requires_grad:
-            raise FateSplatError("fs_flame_backward produces no gradient for expression / pose coefficients "
-                                 "(FateAvatar does not optimise them); detach them before the call")
         f = lambda t: None if t is None else t.detach().contiguous().float()
         b, p = f(betas).reshape(-1), f(pose).reshape(-1)
         dv, ds, dp = f(delta_vertex), f(delta_shapedirs), f(delta_posedirs)
         r = flame_forward_raw(b, p, model["v_template"], model["shapedirs"], model["posedirs"], model["J_regressor"],
                               model["parents"], model["lbs_weights"], dv, ds, dp, l0=l0, want_orig=want_orig)
-        ctx.model, ctx.l0, ctx.ws, ctx.betas = model, l0, r["workspace"], b
+        ctx.model, ctx.l0, ctx.ws, ctx.betas, ctx.pose = model, l0, r["workspace"], b, p
+        ctx.deltas = (ds, dp)  # only read again when the coefficients themselves are being optimised
+        ctx.in_shapes = (betas.shape, pose.shape)
         ctx.have = (delta_vertex is not None, delta_shapedirs is not None, delta_posedirs is not None)
         outs = (r["verts"], r["pose_feature"], r["transforms"])
         if want_orig:
@@ -133,11 +132,36 @@ class _FlameLBS(torch.autograd.Function):
         m = ctx.model
         V, L = m["v_template"].shape[0], m["shapedirs"].shape[-1]
         want = tuple(h and ctx.needs_input_grad[2 + i] for i, h in enumerate(ctx.have))
-        if g_verts is None or not any(want):
+        want_b, want_p = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if g_verts is None or not (any(want) or want_b or want_p):
             return (None,) * 8
         gdv, gds, gdp = flame_backward_raw(ctx.betas, m["J_regressor"], m["parents"], m["lbs_weights"], ctx.ws,
                                            g_verts.contiguous().float().reshape(V, 3), (V, L), l0=ctx.l0, want=want)
-        return None, None, gdv, gds, gdp, None, None, None
+        gb = gp = None
+        if want_b or want_p:  # per-frame tracking optimisation (train/base.py:113-151)
+            gb, gp = flame_backward_coeffs_raw(m, ctx.pose, ctx.deltas[0], ctx.deltas[1], ctx.ws, (V, L), l0=ctx.l0,
+                                               want=(want_b, want_p))
+            gb = gb.reshape(ctx.in_shapes[0]) if gb is not None else None
+            gp = gp.reshape(ctx.in_shapes[1]) if gp is not None else None
+        return gb, gp, gdv, gds, gdp, None, None, None
+
+
+def flame_backward_coeffs_raw(model, pose, delta_shapedirs, delta_posedirs, workspace, shapes, l0=0, want=(True, True)):
+    """One fs_flame_backward_coeffs call (after flame_backward_raw on the same workspace): gradients of the
+    blendshape coefficients [L] (zeros below l0) and of the axis-angle pose [J*3]."""
+    lib = _lib.load()
+    dev = pose.device
+    V, L = shapes
+    pc, J = _parents_c(model["parents"])
+    gb = torch.empty((L,), device=dev) if want[0] else None
+    gp = torch.empty((J * 3,), device=dev) if want[1] else None
+    with _lib.on_device(dev):
+        rc = lib.fs_flame_backward_coeffs(V, L, int(l0), J, pc, pose.data_ptr(), model["shapedirs"].data_ptr(),
+                                          _ptr(delta_shapedirs), model["posedirs"].data_ptr(), _ptr(delta_posedirs),
+                                          model["J_regressor"].data_ptr(), workspace.data_ptr(), workspace.numel(),
+                                          _ptr(gb), _ptr(gp), _lib.stream_ptr(dev))
+    _lib.check(rc, "fs_flame_backward_coeffs")
+    return gb, gp
 
 
 def model_tensors(flame_module):

@@ -180,7 +180,10 @@ int fs_pose_backward(int N, int V, int F, const float* d_verts, const long long*
  * grad = pose_feature (x) dL_dv_posed) for callers that all-reduce 62 KB instead of 26 MB;
  * d_factor_header (optional, [L + (J-1)*9]) receives [betas | pose_feature], the head of the factor record of
  * fs_flame_expand_grads, so a rank's whole record is produced by this one call.
- * Gradients w.r.t. betas and pose are not produced (FateAvatar does not optimise them on INSTA data).
+ * fs_flame_backward_coeffs (optional, call it after fs_flame_backward on the same workspace) adds the gradients of
+ * the COEFFICIENTS for callers that optimise per-frame tracking (train/base.py:113-151; off for INSTA data):
+ * dL/dbetas [L] (entries below l0 are written as 0: the caller declared them constant) and dL/dpose [J*3],
+ * through the blendshapes, the joint regression, the pose correctives, the kinematic chain and Rodrigues.
  */
 #define FS_FLAME_MAX_JOINTS 8
 size_t fs_flame_workspace_bytes(int V);
@@ -190,6 +193,10 @@ int fs_flame_forward(int V, int L, int l0, int J, const int* parents_host, const
                      const float* d_J_regressor, const float* d_lbs_weights, float* d_verts, float* d_verts_orig,
                      float* d_pose_feature, float* d_transforms, float* d_transforms_orig, void* d_workspace,
                      size_t workspace_bytes, void* stream);
+int fs_flame_backward_coeffs(int V, int L, int l0, int J, const int* parents_host, const float* d_pose,
+                             const float* d_shapedirs, const float* d_delta_shapedirs, const float* d_posedirs,
+                             const float* d_delta_posedirs, const float* d_J_regressor, void* d_workspace,
+                             size_t workspace_bytes, float* d_dL_dbetas, float* d_dL_dpose, void* stream);
 int fs_flame_backward(int V, int L, int l0, int J, const int* parents_host, const float* d_betas,
                       const float* d_J_regressor, const float* d_lbs_weights, const float* d_dL_dverts,
                       void* d_workspace, size_t workspace_bytes, float* d_dL_ddelta_vertex,

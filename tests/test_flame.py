@@ -197,10 +197,45 @@ def test_attach_rebinds_reference_flame_module_methods(cuda_device):
     # a different pose is not served from the cache
     v2, _, _ = mod.forward(expression_params=expr, full_pose=pose * 0.5)
     assert np.abs(v2[0].cpu().numpy() - o0["verts"]).max() > 1e-5
-    with pytest.raises(FateSplatError):
-        mod.forward_with_delta_blendshape(expr.clone().requires_grad_(True), pose, leaves["delta_shapedirs"], leaves["delta_posedirs"],
-                                          leaves["delta_vertex"])
     assert lc0 >= 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["flame_l0_300", "dense_betas_l0_0", "three_joints_odd_sizes"])
+def test_expression_and_pose_coefficient_gradients(case, cuda_device):
+    """fs_flame_backward_coeffs vs float64 autograd of the oracle: dL/dbetas (through blendshapes + joint regression)
+    and dL/dpose (through pose correctives, kinematic chain and Rodrigues)."""
+    from fateavatar_b200 import flame
+
+    if case == "flame_l0_300":
+        f, l0 = scenes.flame_inputs(seed=12, V=500), 300
+    elif case == "dense_betas_l0_0":
+        f, l0 = scenes.flame_inputs(seed=13, V=90), 0
+        f["betas"][:300] = 0.2 * np.random.default_rng(2).standard_normal(300).astype(np.float32)
+    else:
+        f, l0 = scenes.flame_inputs(seed=14, V=61, n_shape=5, n_exp=9, J=3), 5
+    V = f["v_template"].shape[0]
+    g = np.random.default_rng(8).standard_normal((V, 3)).astype(np.float32)
+    # oracle
+    m64 = _model(f, torch.float64)
+    t64 = lambda k: torch.from_numpy(f[k]).double()
+    b64, p64 = t64("betas").requires_grad_(True), t64("pose").requires_grad_(True)
+    v64, _, _ = fo.forward_with_delta_blendshape(m64, b64, p64, t64("delta_shapedirs"), t64("delta_posedirs"), t64("delta_vertex"))
+    (v64 * torch.from_numpy(g).double()).sum().backward()
+    want_b = b64.grad.numpy().copy()
+    want_b[:l0] = 0.0  # coefficients below l0 are declared constant
+    # kernels, through autograd
+    m = _model(f, torch.float32, cuda_device)
+    m["parents"] = [int(x) for x in f["parents"]]
+    t = lambda k: torch.from_numpy(f[k]).to(cuda_device)
+    betas, pose = t("betas")[None].requires_grad_(True), t("pose")[None].requires_grad_(True)
+    dv = t("delta_vertex").requires_grad_(True)
+    outs = flame.flame_lbs(m, betas, pose, t("delta_shapedirs"), t("delta_posedirs"), dv, l0=l0)
+    (outs[0][0] * torch.from_numpy(g).to(cuda_device)).sum().backward()
+    got_b, got_p = betas.grad[0].cpu().numpy(), pose.grad[0].cpu().numpy()
+    assert betas.grad.shape == betas.shape and pose.grad.shape == pose.shape and dv.grad is not None
+    assert np.abs(got_b - want_b).max() <= 2e-5 * np.abs(want_b).max(), (np.abs(got_b - want_b).max(), np.abs(want_b).max())
+    assert np.abs(got_p - p64.grad.numpy()).max() <= 2e-5 * np.abs(p64.grad.numpy()).max()
 
 
 @pytest.mark.gpu
