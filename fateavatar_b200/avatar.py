@@ -1,0 +1,128 @@
+"""Caller-side mirror of `FateAvatar.forward` (model/fateavatar.py:196-298) on the fused operators.
+
+The reference's per-frame forward is: build a Camera (two CPU 4x4 inverses and a host round trip per frame,
+volume_rendering/camera_3dgs.py:53-72), FLAME skinning twice, ~60 torch ops that place the splats on the mesh, then
+render().  `forward_frame(model, input)` produces the same output dict from the same model attributes with
+
+    FrameCamera        closed-form view / projection / camera centre on the device (no inverse, no host sync)
+    flame.flame_lbs    both FLAME meshes in one pass                                  (fs_flame_forward)
+    pose.pose_splats   face frames, quaternions, barycentric positions, activations   (fs_pose_forward)
+    GaussianRasterizer                                                               (fs_forward)
+
+and `attach(model)` rebinds `model.forward` (plus the FLAME methods and the densification statistics) on an existing
+reference FateAvatar instance, so train/iteration.py runs unchanged.  Everything stays differentiable through the
+library's autograd Functions.  CUDA only.
+"""
+import math
+
+import torch
+
+from . import densify as _densify
+from . import flame as _flame
+from . import pose as _pose
+from . import rasterizer as _rasterizer
+
+
+class FrameCamera:
+    """Attributes render() reads from volume_rendering/camera_3dgs.py:Camera, computed in closed form.
+
+    The reference builds Rt = [[R^T, T], [0, 1]], inverts it twice on the CPU (getWorld2View2_torch with zero
+    translate / unit scale is the identity on Rt) and inverts the view matrix once more for the camera centre.
+    Here world_view_transform = Rt^T directly and camera_center = -R T, equal to the reference's up to the fp32
+    rounding of its inverses."""
+
+    _proj_cache = {}
+
+    def __init__(self, R, T, FoVx, FoVy, img_res, znear=0.01, zfar=100.0):
+        R, T = R.reshape(3, 3), T.reshape(3)
+        dev = R.device
+        self.FoVx, self.FoVy = float(FoVx), float(FoVy)
+        self.image_height, self.image_width = int(img_res[0]), int(img_res[1])
+        self.znear, self.zfar = znear, zfar
+        view = torch.zeros(4, 4, device=dev, dtype=torch.float32)
+        view[:3, :3] = R            # (Rt^T)[:3,:3] = (R^T)^T
+        view[3, :3] = T             # (Rt^T)[3,:3]  = T
+        view[3, 3] = 1.0
+        self.world_view_transform = view
+        key = (self.FoVx, self.FoVy, znear, zfar, str(dev))
+        proj = FrameCamera._proj_cache.get(key)
+        if proj is None:  # tools/gs_utils/graphics_utils.py:64-84, transposed
+            tx, ty = math.tan(self.FoVx / 2), math.tan(self.FoVy / 2)
+            P = torch.zeros(4, 4)
+            P[0, 0], P[1, 1] = 1.0 / tx, 1.0 / ty
+            P[3, 2] = 1.0
+            P[2, 2] = zfar / (zfar - znear)
+            P[2, 3] = -(zfar * znear) / (zfar - znear)
+            proj = P.t().contiguous().to(dev)
+            FrameCamera._proj_cache[key] = proj
+        self.projection_matrix = proj
+        self.full_proj_transform = view @ proj
+        self.camera_center = -(R.to(torch.float32) @ T.to(torch.float32))
+
+
+def quaternion_to_axis_angle(q):
+    """pytorch3d.transforms.quaternion_to_axis_angle (published 0.7.x algorithm; the package is not vendored by the
+    reference, so this restatement is parity-unpinned like the other quaternion helpers)."""
+    norms = torch.norm(q[..., 1:], p=2, dim=-1, keepdim=True)
+    half = torch.atan2(norms, q[..., :1])
+    angles = 2 * half
+    small = angles.abs() < 1e-6
+    s = torch.where(small, 0.5 - (angles * angles) / 48, torch.sin(half) / torch.where(small, torch.ones_like(angles), angles))
+    return q[..., 1:] / s
+
+
+def forward_frame(model, input):
+    """`model`: an object with FateAvatar's attributes (flame, faces, face_index, bary_coords, face_scaling_canonical,
+    _scaling, _rotation, _offset, _opacity, _features_dc, delta_shapedirs, delta_posedirs, delta_vertex, cfg_model,
+    shell_len, bg_color, img_res, device); `input`: the dataset's dict (cam_pose, fovx, fovy, flame_pose, expression).
+    Returns the dict of model/fateavatar.py:280-296."""
+    cam_pose = input["cam_pose"]
+    camera = FrameCamera(cam_pose[:, :3, :3], cam_pose[:, :3, 3], input["fovx"][0], input["fovy"][0], model.img_res)
+    flame_pose, expression = input["flame_pose"], input["expression"]
+    bs = flame_pose.shape[0]
+    if bs != 1:
+        raise _rasterizer.FateSplatError("forward_frame renders one frame per call (the reference's batch size)")
+    cfg = model.cfg_model
+    fm = getattr(model, "_fs_flame_model", None)
+    if fm is None:
+        fm = model._fs_flame_model = _flame.model_tensors(model.flame)
+    n_shape, n_exp = int(model.flame.n_shape), int(model.flame.n_exp)
+    e = expression[:, :n_exp]
+    betas = torch.cat([torch.zeros(1, n_shape, device=e.device, dtype=e.dtype), e], dim=1)  # flame/FLAME.py:180
+    verts, _, _, verts_orig, _ = _flame.flame_lbs(
+        fm, betas, flame_pose,
+        model.delta_shapedirs if cfg.delta_blendshape else None, model.delta_posedirs if cfg.delta_blendshape else None,
+        model.delta_vertex if cfg.delta_vertex else None, l0=n_shape, want_orig=True)
+    xyz, scales, rots, opac = _pose.pose_splats(verts, model.faces, model.face_index, model.bary_coords,
+                                                model.face_scaling_canonical, model._scaling, model._rotation,
+                                                model._offset, model._opacity, shell_len=model.shell_len,
+                                                resize_scale=bool(cfg.resize_scale))
+    screenspace = torch.zeros_like(xyz, requires_grad=True)  # render_3dgs.py:22-27: .grad feeds the densifier
+    settings = _rasterizer.GaussianRasterizationSettings(
+        image_height=camera.image_height, image_width=camera.image_width, tanfovx=math.tan(camera.FoVx * 0.5),
+        tanfovy=math.tan(camera.FoVy * 0.5), bg=model.bg_color.to(xyz.device), scale_modifier=1.0,
+        viewmatrix=camera.world_view_transform, projmatrix=camera.full_proj_transform, sh_degree=0,
+        campos=camera.camera_center, prefiltered=False, debug=False)
+    image, radii = _rasterizer.GaussianRasterizer(settings)(means3D=xyz, means2D=screenspace, shs=model._features_dc,
+                                                           opacities=opac, scales=scales, rotations=rots)
+    return {
+        "rgb_image": image[None],
+        "scale": torch.exp(model._scaling),
+        "raw_rot": quaternion_to_axis_angle(model._rotation),
+        "viewspace_points": [screenspace],
+        "visibility_filter": [radii > 0],
+        "radii": [radii],
+        "bs": bs,
+        "verts": verts,
+        "verts_orig": verts_orig,
+        "faces": model.faces,
+    }
+
+
+def attach(model):
+    """Rebind the per-frame hot path of an existing reference FateAvatar instance: `forward`, the two FLAME methods and
+    `_add_densification_stats`.  Nothing else of the model (densify / prune / checkpoints / inference) is touched."""
+    _flame.attach(model.flame)
+    _densify.attach(model)
+    model.forward = lambda input: forward_frame(model, input)
+    return model
