@@ -459,31 +459,38 @@ def main():
     # target image.
     R.set_async(False)
     host = []
+    cam_pose = np.eye(4, dtype=np.float32)  # what the dataset yields (train/dataset.py): c2w rotation, w2c translation
+    cam_pose[:3, :3], cam_pose[:3, 3] = np.diag([1.0, -1.0, -1.0]), [0.0, 0.0, 1.25]
     for f in frames:
-        c = f["camera"]
         h = dict(expression=torch.from_numpy(f["betas"][n_shape:])[None], flame_pose=torch.from_numpy(f["pose"])[None],
-                 view=torch.from_numpy(c["viewmatrix"]), proj=torch.from_numpy(c["projmatrix"]),
-                 campos=torch.from_numpy(c["campos"]), target=torch.rand(3, args.res, args.res))
+                 cam_pose=torch.from_numpy(cam_pose)[None], target=torch.rand(3, args.res, args.res))
         host.append({k: v.contiguous().pin_memory() for k, v in h.items()})
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
     out_loss = torch.empty(1).pin_memory()
     d2h = 4
-    leaves = [p_.clone().requires_grad_(True) for p_ in params] + [shs.clone().requires_grad_(True)]
-    dleaves = {k: v.clone().requires_grad_(True) for k, v in fdelta.items()}
-    zeros_shape = torch.zeros(1, n_shape, device=dev)
+    leaves = [torch.nn.Parameter(p_.clone()) for p_ in params] + [torch.nn.Parameter(shs.clone())]
+    dleaves = {k: torch.nn.Parameter(v.clone()) for k, v in fdelta.items()}
+    # a FateAvatar look-alike: the attributes model/fateavatar.py keeps, driven through the caller-level mirror
+    # fateavatar_b200.avatar.forward_frame (= FateAvatar.forward: camera, FLAME x2, splat placement, render)
+    import types
+
+    from fateavatar_b200 import avatar
+
+    flame_mod = types.SimpleNamespace(n_shape=n_shape, n_exp=L - n_shape, parents=torch.tensor(f0["parents"]),
+                                      **{k: fmodel[k] for k in FLAME_KEYS})
+    model = types.SimpleNamespace(
+        flame=flame_mod, faces=faces, face_index=fidx, bary_coords=bary, face_scaling_canonical=canon,
+        _scaling=leaves[0], _rotation=leaves[1], _offset=leaves[2], _opacity=leaves[3], _features_dc=leaves[4],
+        delta_shapedirs=dleaves["delta_shapedirs"], delta_posedirs=dleaves["delta_posedirs"],
+        delta_vertex=dleaves["delta_vertex"], shell_len=f0["shell_len"], bg_color=bg, img_res=(args.res, args.res),
+        cfg_model=types.SimpleNamespace(delta_blendshape=True, delta_vertex=True, resize_scale=True))
+    fov = [0.35]
 
     def frame(d):
-        """One frame through the public operator API under autograd; `d` holds this frame's inputs on the device."""
-        full_betas = torch.cat([zeros_shape, d["expression"]], dim=1)  # flame/FLAME.py:180
-        vts, _, _, vts_orig, _ = flame.flame_lbs(fmodel, full_betas, d["flame_pose"], dleaves["delta_shapedirs"],
-                                                 dleaves["delta_posedirs"], dleaves["delta_vertex"], l0=n_shape)
-        xyz, sc, ro, op = pose.pose_splats(vts, faces, fidx, bary, canon, *leaves[:4], shell_len=f0["shell_len"])
-        settings = R.GaussianRasterizationSettings(args.res, args.res, cam["tanfovx"], cam["tanfovy"], bg, 1.0, d["view"],
-                                                   d["proj"], 0, d["campos"], False, False)
-        screen = torch.zeros_like(xyz, requires_grad=True)
-        img, radii = R.GaussianRasterizer(settings)(means3D=xyz, means2D=screen, shs=leaves[4], opacities=op, scales=sc,
-                                                    rotations=ro)
-        loss = (img - d["target"]).abs().mean()
+        """One training frame through the public API under autograd; `d` holds this frame's inputs on the device."""
+        out = avatar.forward_frame(model, dict(cam_pose=d["cam_pose"], fovx=fov, fovy=fov, flame_pose=d["flame_pose"],
+                                               expression=d["expression"]))
+        loss = (out["rgb_image"][0] - d["target"]).abs().mean()
         loss.backward()
         return {"loss": loss.detach().reshape(1)}  # what a training step reads back (train/trainer.py: loss.item())
 
@@ -537,9 +544,10 @@ def main():
     graph_fps = time_e2e(graph_step, e2e_steps)
     R.set_async(False)
     e2e = {"value": graph_fps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-           "api": "fateavatar_b200.graph.CapturedStep replaying one frame of flame.flame_lbs + pose.pose_splats + "
-                  "GaussianRasterizer (drop-in operator API) under autograd with an L1 loss; host inputs (expression, pose, "
-                  "camera, target image) copied in and the loss copied out through pinned memory every step",
+           "api": "fateavatar_b200.graph.CapturedStep replaying one frame of fateavatar_b200.avatar.forward_frame (the mirror "
+                  "of FateAvatar.forward: camera, FLAME skinning, splat placement, GaussianRasterizer) under autograd with an "
+                  "L1 loss; host inputs (expression, pose, camera pose, target image) copied in and the loss copied out "
+                  "through pinned memory every step",
            "eager_value": eager_fps,
            "eager_api": "the same frame with every operator call issued from Python (default synchronous mode)"}
 

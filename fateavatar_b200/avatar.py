@@ -32,6 +32,7 @@ class FrameCamera:
     rounding of its inverses."""
 
     _proj_cache = {}
+    _const_cache = {}
 
     def __init__(self, R, T, FoVx, FoVy, img_res, znear=0.01, zfar=100.0):
         R, T = R.reshape(3, 3), T.reshape(3)
@@ -39,10 +40,13 @@ class FrameCamera:
         self.FoVx, self.FoVy = float(FoVx), float(FoVy)
         self.image_height, self.image_width = int(img_res[0]), int(img_res[1])
         self.znear, self.zfar = znear, zfar
-        view = torch.zeros(4, 4, device=dev, dtype=torch.float32)
-        view[:3, :3] = R            # (Rt^T)[:3,:3] = (R^T)^T
-        view[3, :3] = T             # (Rt^T)[3,:3]  = T
-        view[3, 3] = 1.0
+        consts = FrameCamera._const_cache.get(str(dev))
+        if consts is None:  # built once per device, outside any CUDA-graph capture (warm-up frames come first)
+            consts = (torch.zeros(3, 1, device=dev), torch.ones(1, 1, device=dev))
+            FrameCamera._const_cache[str(dev)] = consts
+        R32, T32 = R.to(torch.float32), T.to(torch.float32)
+        # world_view_transform = Rt^T = [[R, 0], [T, 1]]; assembled from device tensors only (capture-safe)
+        view = torch.cat([torch.cat([R32, consts[0]], dim=1), torch.cat([T32[None], consts[1]], dim=1)], dim=0)
         self.world_view_transform = view
         key = (self.FoVx, self.FoVy, znear, zfar, str(dev))
         proj = FrameCamera._proj_cache.get(key)
@@ -57,7 +61,7 @@ class FrameCamera:
             FrameCamera._proj_cache[key] = proj
         self.projection_matrix = proj
         self.full_proj_transform = view @ proj
-        self.camera_center = -(R.to(torch.float32) @ T.to(torch.float32))
+        self.camera_center = -(R32 @ T32)
 
 
 def quaternion_to_axis_angle(q):
