@@ -63,6 +63,8 @@ CASES = {
     "sh1": lambda: scenes.head_scene(P=3000, W=96, H=96, sh_degree=1, scale_mult=6.0, seed=4),
     "sh2": lambda: scenes.head_scene(P=3000, W=96, H=96, sh_degree=2, scale_mult=6.0, seed=5),
     "sh3": lambda: scenes.head_scene(P=3000, W=96, H=96, sh_degree=3, scale_mult=6.0, seed=6),
+    # active degree below the stored maximum (gaussianavatars.py:157): 16 coefficients per splat, only (1+1)^2 used
+    "sh_active1_of_3": lambda: dict(scenes.head_scene(P=3000, W=96, H=96, sh_degree=3, scale_mult=6.0, seed=14), sh_degree=1),
     "single_gaussian": lambda: scenes.config1_scene(P=1, W=64, H=64, seed=9),
     "p33": lambda: scenes.config1_scene(P=33, W=64, H=64, seed=10),
     "smoke_scene_5k_128": lambda: scenes.head_scene(P=5000, W=128, H=128, scale_mult=5.0, seed=1),  # has fragile pixels
