@@ -1,7 +1,16 @@
 """fateavatar_b200 -- sm_100a 3D-Gaussian-splatting operators behind FateAvatar's rasterizer API.
 
-The package holds only the hot path: the CUDA kernels + C ABI (csrc/, lib/),
-and the Python mirror of the reference operator interface (rasterizer.py, knn.py, pose.py, render.py).
+The package holds only the hot path: the CUDA kernels + C ABI (csrc/, lib/) and the Python
+mirrors of the reference's interfaces for that path:
+
+    rasterizer.py, knn.py   diff_gaussian_rasterization / simple_knn operator API          (fs_forward, fs_backward, ...)
+    render.py               volume_rendering/render_3dgs.py:render
+    flame.py                flame/FLAME.py forward / forward_with_delta_blendshape          (fs_flame_*)
+    pose.py                 the per-splat placement block of model/fateavatar.py:225-258     (fs_pose_*)
+    densify.py              _add_densification_stats                                         (fs_densify_stats)
+    avatar.py               FateAvatar.forward as one call (forward_frame / attach)
+    graph.py                whole-frame CUDA-graph capture / replay (CapturedStep)
+    exchange.py, parallel.py  frame-sharded multi-GPU: peer-memory gradient exchange, sampler, densify sync
 
     import fateavatar_b200; fateavatar_b200.install()
     # from here on `import diff_gaussian_rasterization` / `from simple_knn._C import distCUDA2`
