@@ -195,7 +195,7 @@ def test_autograd_through_render_mirror(cuda_device):
     assert np.array_equal(out["radii"].cpu().numpy(), o["radii"])
 
 
-@pytest.mark.parametrize("path", sorted(p for p in glob.glob(os.path.join(HERE, "golden", "*.npz")) if not os.path.basename(p).startswith("flame")) or [None])
+@pytest.mark.parametrize("path", sorted(p for p in glob.glob(os.path.join(HERE, "golden", "*.npz")) if not os.path.basename(p).startswith(("flame", "pose"))) or [None])
 def test_against_reference_golden(path, cuda_device):
     if path is None:
         pytest.skip("no golden fixtures committed yet")

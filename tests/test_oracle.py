@@ -83,7 +83,7 @@ def test_oracle_mark_visible_and_knn():
     assert np.allclose(small, np.sort(d2, axis=1)[:, :3].mean(1), rtol=1e-5)
 
 
-GOLDEN = sorted(p for p in glob.glob(os.path.join(HERE, "golden", "*.npz")) if not os.path.basename(p).startswith("flame"))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(HERE, "golden", "*.npz")) if not os.path.basename(p).startswith(("flame", "pose")))
 
 
 @pytest.mark.parametrize("path", GOLDEN or [None])

@@ -130,3 +130,15 @@ def test_densification_stats_kernel_matches_reference_expression(cuda_device):
     assert float(((model.xyz_gradient_accum.cpu() - ref_a).abs() / ref_a.abs().clamp(min=1.0)).max()) <= 3e-7
     with pytest.raises(Exception):
         densify.densify_stats_raw(ref_a, ref_d, grad, filt)  # CPU tensors: no CPU path
+
+
+def test_oracle_mesh_functions_match_golden_fixture_from_reference():
+    """tests/golden/pose_mesh_small.npz was made by the reference's own mesh_compute.py (make_pose_golden.py)."""
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pose_mesh_small.npz"))
+    p = scenes.pose_inputs(N=10, seed=31)
+    verts, faces = torch.from_numpy(p["verts"])[None], torch.from_numpy(p["faces"])
+    orient, scale = po.compute_face_orientation(verts, faces)
+    normals = po.compute_face_normals(verts, faces)
+    _, canon = po.compute_face_orientation(torch.from_numpy(p["canon_verts"])[None], faces)
+    assert np.array_equal(orient[0, ::7].numpy(), gold["orient"]) and np.array_equal(scale[0, ::7].numpy(), gold["scale"])
+    assert np.array_equal(normals[0, ::7].numpy(), gold["normals"]) and np.array_equal(canon[0, ::7].numpy(), gold["canon_scale"])
