@@ -1,0 +1,124 @@
+"""Property tests of the oracle on random and deliberately degenerate scenes (CPU, hypothesis): the invariants any
+implementation of the reference algorithm must satisfy -- SURVEY section 4's "property" layer.  The GPU parity tests
+compare the kernels with this oracle; these tests make sure the oracle itself does not break at the edges."""
+import numpy as np
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
+
+from fateavatar_b200 import scenes
+from oracle import oracle as orc
+from util import oracle_forward
+
+
+@st.composite
+def scene_strategy(draw):
+    P = draw(st.integers(1, 120))
+    W, H = draw(st.integers(1, 48)), draw(st.integers(1, 40))          # ragged images (forward.cu:285)
+    seed = draw(st.integers(0, 10 ** 6))
+    sc = scenes.config1_scene(P=P, W=W, H=H, seed=seed)
+    rng = np.random.default_rng(seed)
+    mode = draw(st.sampled_from(["plain", "flat", "huge", "opaque", "transparent", "behind", "bright", "edge"]))
+    if mode == "flat":          # one scale ~0: near-singular 3D covariance, det of the 2D conic stays > 0 via the +0.3
+        sc["scales"][:, draw(st.integers(0, 2))] = 1e-12
+    elif mode == "huge":        # splats much larger than the image: every tile touched, rect clamps
+        sc["scales"] *= 200.0
+    elif mode == "opaque":      # alpha saturates at 0.99, early termination after one or two splats
+        sc["opacities"][:] = 1.0
+        sc["scales"] *= 20.0
+    elif mode == "transparent":  # alpha < 1/255 everywhere: nothing contributes
+        sc["opacities"][:] = 1e-3
+    elif mode == "behind":      # some / all splats behind the near plane
+        sc["means3D"][: max(1, P // 2), 2] += 10.0
+    elif mode == "bright":      # SH colours far outside [0, 1]: the max(0, .) clamp and its flags
+        sc["shs"] = (sc["shs"] + rng.normal(0, 8.0, sc["shs"].shape)).astype(np.float32)
+    elif mode == "edge":        # centres far off-axis: the 1.3 tan(fov) frustum clamp of the Jacobian
+        sc["means3D"][:, :2] *= 30.0
+    return sc, mode
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+@given(scene_strategy())
+def test_forward_invariants(case):
+    sc, mode = case
+    o = oracle_forward(orc, sc)
+    P = sc["means3D"].shape[0]
+    cam = sc["camera"]
+    H, W = cam["H"], cam["W"]
+    gx, gy = (W + 15) // 16, (H + 15) // 16
+    vis = o["radii"] > 0
+    # bookkeeping
+    assert o["R"] == int(o["tiles_touched"].sum()) and (o["tiles_touched"][~vis] == 0).all()
+    assert (o["tiles_touched"] <= gx * gy).all()
+    rng = o["ranges"].astype(np.int64)
+    lens = rng[:, 1] - rng[:, 0]
+    assert (lens >= 0).all() and int(lens.sum()) == o["R"]
+    # every list is sorted by (depth bits, id) and holds only visible splats
+    db = o["depths"].view(np.uint32)
+    for t in np.nonzero(lens)[0]:
+        ids = o["point_list"][rng[t, 0]:rng[t, 1]].astype(np.int64)
+        assert vis[ids].all()
+        key = (db[ids].astype(np.uint64) << np.uint64(32)) | ids.astype(np.uint64)
+        assert (key[1:] > key[:-1]).all()
+    # per-pixel results
+    assert np.isfinite(o["color"]).all() and np.isfinite(o["final_T"]).all()
+    assert (o["final_T"] > 0).all() and (o["final_T"] <= 1.0).all()
+    tile_of = (np.arange(H)[:, None] // 16) * gx + (np.arange(W)[None, :] // 16)
+    assert (o["n_contrib"].astype(np.int64) <= lens[tile_of]).all()
+    untouched = o["n_contrib"] == 0
+    assert np.allclose(o["color"][:, untouched], sc["bg"][:, None]) and (o["final_T"][untouched] == 1.0).all()
+    assert (o["rgb"][vis] >= 0).all()                      # clamped SH colour
+    if mode == "transparent":
+        assert untouched.all()
+    if mode == "behind":
+        assert not vis[: max(1, P // 2)].any()
+    if mode == "opaque" and (~untouched).any():
+        assert o["final_T"][~untouched].min() < 0.02        # one saturated splat leaves T = 0.01
+
+
+@settings(max_examples=15, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+@given(scene_strategy())
+def test_backward_is_finite_linear_and_silent_where_nothing_was_drawn(case):
+    sc, mode = case
+    o = oracle_forward(orc, sc)
+    cam = sc["camera"]
+    g1 = np.random.default_rng(1).standard_normal((3, cam["H"], cam["W"])).astype(np.float32)
+    g2 = np.random.default_rng(2).standard_normal((3, cam["H"], cam["W"])).astype(np.float32)
+    a, b, ab = orc.backward(o, g1), orc.backward(o, g2), orc.backward(o, (g1 + 2 * g2).astype(np.float32))
+    vis = o["radii"] > 0
+    for k in ("dL_dmeans3D", "dL_dscales", "dL_drotations", "dL_dopacity", "dL_dsh", "dL_dmeans2D"):
+        assert np.isfinite(a[k]).all(), k
+        assert not a[k][~vis].any(), k                     # culled splats receive no gradient
+        lin = a[k].astype(np.float64) + 2 * b[k].astype(np.float64)
+        scale = max(np.abs(lin).max(), np.abs(a[k]).max(), np.abs(b[k]).max(), 1e-20)
+        assert np.abs(ab[k] - lin).max() <= 2e-4 * scale, k  # the backward is linear in the upstream gradient
+    zero = orc.backward(o, np.zeros_like(g1))
+    assert all(not zero[k].any() for k in zero)
+
+
+# ---- the same scene family on the GPU (opt-in) ------------------------------------------------------------------------
+# Written in the last GPU-less hours of round 1 and therefore NOT yet run on a B200: it only executes when
+# FATESPLAT_PROPERTY_GPU=1 so that an unvalidated test cannot turn the suite red.  Enable it by default after one run.
+import os  # noqa: E402
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("FATESPLAT_PROPERTY_GPU", "0") != "1", reason="opt-in until validated on a B200")
+@settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large,
+                                                                 HealthCheck.function_scoped_fixture])
+@given(case=scene_strategy())
+def test_kernels_match_oracle_on_degenerate_scenes(case, cuda_device):
+    from test_gpu_parity import check_forward_vs_oracle, run_new
+    from util import GRAD_NAMES, assert_grad_close
+
+    sc, mode = case
+    sc = dict(sc, sh_degree=0)
+    o = oracle_forward(orc, sc)
+    cam = sc["camera"]
+    dpix = orc.mask_fragile(o, np.random.default_rng(3).standard_normal((3, cam["H"], cam["W"])).astype(np.float32))
+    color, radii, st, taps, grads = run_new(sc, cuda_device, dpix=dpix)
+    check_forward_vs_oracle(color, radii, st, taps, o)
+    og = orc.backward(o, dpix)
+    for k in GRAD_NAMES:
+        assert_grad_close(k, grads[k].cpu().numpy(), og[k])
