@@ -160,3 +160,45 @@ def test_parallel_sampler_is_pure_host_logic():
         parallel.FrameShardSampler(10, 3, 3)
     g1, g2 = parallel.synced_generator("cpu", 5, 100), parallel.synced_generator("cpu", 5, 100)
     assert torch.equal(torch.rand(4, generator=g1), torch.rand(4, generator=g2))
+
+
+def test_uv_densify_with_synchronised_generator_keeps_replicas_identical():
+    """parallel.uv_densify = FateAvatar._uv_densify (model/fateavatar.py:610-670) with an explicit generator."""
+    import types
+
+    from fateavatar_b200 import parallel
+
+    def make_replica():
+        g = torch.Generator().manual_seed(3)
+        N = 50
+        P = lambda *s: torch.nn.Parameter(torch.randn(*s, generator=g))
+        m = types.SimpleNamespace(_opacity=P(N, 1), _offset=P(N, 1), _features_dc=P(N, 1, 3), _rotation=P(N, 4), _scaling=P(N, 3),
+                                  face_index=torch.randint(0, 20, (N,), generator=g), bary_coords=torch.rand(N, 3, generator=g),
+                                  xyz_gradient_accum=torch.rand(N, 1, generator=g), denom=torch.ones(N, 1),
+                                  max_radii2D=torch.ones(N), sample_flag=torch.zeros(N), num_points=N)
+        opt = torch.optim.Adam([{"params": [getattr(m, a)], "name": n, "lr": 1e-3} for n, a in parallel._ATTR_OF_GROUP.items()])
+        sum((getattr(m, a) ** 2).sum() for a in parallel._ATTR_OF_GROUP.values()).backward()
+        opt.step()  # creates the Adam moments
+        return m, opt
+
+    (a, oa), (b, ob) = make_replica(), make_replica()
+    before = {k: getattr(a, v).detach().clone() for k, v in parallel._ATTR_OF_GROUP.items()}
+    pa = parallel.uv_densify(a, oa, 17, generator=parallel.synced_generator("cpu", 9, 3000))
+    pb = parallel.uv_densify(b, ob, 17, generator=parallel.synced_generator("cpu", 9, 3000))
+    assert torch.equal(pa, pb) and a.num_points == b.num_points == 67
+    for name, attr in parallel._ATTR_OF_GROUP.items():
+        ta, tb = getattr(a, attr), getattr(b, attr)
+        assert isinstance(ta, torch.nn.Parameter) and ta.requires_grad and ta.shape[0] == 67 and torch.equal(ta, tb)
+        assert torch.equal(ta[:50], before[name])                                       # old splats untouched
+        want = before[name][pa] if name != "scaling" else torch.log(torch.exp(before[name][pa]) * 0.75)
+        assert torch.allclose(ta[50:], want)                                            # children copy their parent
+        st = oa.state[ta]
+        assert st["exp_avg"].shape == ta.shape and not st["exp_avg"][50:].any() and st["exp_avg"][:50].any()
+        assert any(g["params"][0] is ta for g in oa.param_groups)
+    assert torch.equal(a.face_index[50:], a.face_index[pa]) and torch.equal(a.bary_coords, b.bary_coords)
+    assert torch.allclose(a.bary_coords[50:].sum(-1), torch.ones(17)) and (a.bary_coords[50:] >= 0).all()
+    assert a.xyz_gradient_accum.shape == (67, 1) and not a.xyz_gradient_accum.any() and not a.denom.any()
+    assert a.sample_flag[50:].all() and not a.sample_flag[:50].any() and a.max_radii2D.shape == (67,)
+    oa.zero_grad()
+    sum((getattr(a, v) ** 2).sum() for v in parallel._ATTR_OF_GROUP.values()).backward()
+    oa.step()                                                                            # the optimizer still works
