@@ -21,6 +21,8 @@
 //                               parameter gradients: delta_vertex, delta_posedirs (rank-1: pose_feature (x) g) and
 //                               delta_shapedirs (rank-1: g (x) betas, 24 MB of streaming stores -- the only part of
 //                               the stage that is HBM-bound).
+// plus flame_coeff_partial/final_kernel (optional gradients of the expression / pose coefficients) and
+// flame_expand_kernel (multi-GPU: dense delta gradients from the all-gathered rank-1 factors).
 // Everything is deterministic (no float atomics).  fp32 throughout; sums run in a different order than cuBLAS's
 // so parity with the reference is to tolerance (tests/test_flame.py), not bitwise.
 #include "common.cuh"
