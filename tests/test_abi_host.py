@@ -140,6 +140,11 @@ def test_training_path_entry_points_validate_arguments_before_launching():
     assert lib.fs_flame_expand_grads(2, 10, 8, 0, 36, None, 8 + 36 + 59, 1.0, None, None, None, None) == -1
     assert lib.fs_flame_expand_grads(2, 10, 8, 0, 36, None, 200, 1.0, None, None, None, None) == -1
     assert b"NULL" in lib.fs_last_error()
+    bad_tree = (ctypes.c_int * 5)(-1, 0, 3, 1, 1)
+    ok_tree = (ctypes.c_int * 5)(-1, 0, 1, 1, 1)
+    assert lib.fs_flame_backward_coeffs(10, 8, 0, 5, bad_tree, None, None, None, None, None, None, None, 0, None, None, None) == -1
+    assert lib.fs_flame_backward_coeffs(10, 8, 0, 5, ok_tree, None, None, None, None, None, None, None, 0, None, None, None) == -1
+    assert b"NULL" in lib.fs_last_error()
     # peer-memory exchange: n and offset in whole float4s, at least one address table, rank inside the job
     assert lib.fs_p2p_allreduce(2, None, None, 0, 64, None, None) == -1
     assert lib.fs_p2p_allreduce(2, 4096, None, 0, 63, 4096, None) == -1
