@@ -41,6 +41,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "rendered frames/sec (forward+backward) @512x512, 100k Gaussians"
+PAIRS_FRAME0 = None  # filled by the CPU leg: pixel-splat pair counts of frame 0 under the reference's blend rules
 UNIT = "frames/s"
 N_RING = 8  # distinct frames (inputs + workspaces) cycled through so that every step runs on memory > L2
 
@@ -194,6 +195,11 @@ def cpu_arm(args, frames, seconds, max_frames):
         cpu_pose_and_render(frames[n % len(frames)], dpix, orc, po, fo, torch)
         n += 1
     dt = time.perf_counter() - t0
+    try:  # work counters of the reference blend forward on frame 0 (pairs/s next to the HBM fraction)
+        global PAIRS_FRAME0
+        PAIRS_FRAME0 = orc.pair_counts(cpu_pose_and_render(frames[0], dpix, orc, po, fo, torch))
+    except Exception:
+        PAIRS_FRAME0 = None
     return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{n} frames of the same workload (torch FLAME lbs + pose stage, C oracle rasterizer, forward+backward, "
                       f"{threads} threads) in {dt:.1f} s"}, dt / n
@@ -623,6 +629,18 @@ def main():
     if rank == 0 and world == 1:
         cb, _ = cpu_arm(args, frames, args.cpu_seconds, 60)
 
+    try:
+        if rank == 0 and PAIRS_FRAME0 and stage_us.get("blend_forward"):
+            # the blend kernels are bound by pair evaluation, not bytes: pairs the reference's kernel walks for frame 0
+            # (counted by the oracle in the CPU leg) over this kernel's time, against the SFU bound of SURVEY 8d
+            roofline["pairs"] = dict(PAIRS_FRAME0, blend_forward_us=stage_us["blend_forward"],
+                                     reference_pairs_per_s=PAIRS_FRAME0["walked"] / (stage_us["blend_forward"] * 1e-6),
+                                     sfu_bound_exp_per_s=4.5e12,
+                                     note="reference_pairs_per_s = pairs the reference kernel would evaluate for this "
+                                          "frame divided by OUR blend-forward time; the kernel itself skips most of them "
+                                          "by the alpha >= 1/255 bounding-box cull")
+    except Exception:
+        pass
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,

@@ -170,6 +170,14 @@ def knn_mean_dist2(points):
     return out
 
 
+def pair_counts(st):
+    """(walked, exp_evaluated, contributing) pixel-splat pairs of the reference blend forward for the frame `st`."""
+    c = np.zeros(3, np.uint64)
+    lib().orc_blend_pair_counts(C.c_int(st["W"]), C.c_int(st["H"]), _p(st["ranges"]), _p(st["point_list"]),
+                                _p(st["means2D"]), _p(st["conic_opacity"]), _p(c))
+    return dict(walked=int(c[0]), exp_evaluated=int(c[1]), contributing=int(c[2]))
+
+
 def mask_fragile(o, dL_dpix):
     """Upstream gradient with the oracle's threshold-fragile pixels zeroed.  A fragile pixel's list may gain or lose
     one 1/255-contribution between glibc expf and CUDA expf (see compare_blend); feeding both sides a zero upstream

@@ -373,6 +373,45 @@ static inline float splat_power(float mx, float my, float pxf, float pyf, float 
  * that involve expf (alpha < 1/255, T(1-alpha) < 1e-4) was within rounding distance of its threshold: there a 1-ulp
  * difference between glibc's expf and CUDA's MUFU-based expf can flip the decision, so tests compare such
  * pixels with the looser bound of one dropped 1/255 contribution instead of 1e-5. */
+/* Work counters of the reference blend forward (forward.cu:261-374) for one frame, for the pairs/s figure that sits
+ * next to the HBM roofline: counts[0] = (pixel, list entry) pairs the reference kernel walks until
+ * each pixel terminates, counts[1] = of those, pairs whose exponential is evaluated (power <= 0),
+ * counts[2] = pairs that contribute colour (alpha >= 1/255, applied before termination). */
+void orc_blend_pair_counts(int W, int H, const uint32_t* ranges, const uint32_t* point_list, const float* means2D,
+                           const float* conic_opacity, unsigned long long* counts) {
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    unsigned long long walked = 0, evals = 0, contrib = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : walked, evals, contrib)
+    for (int t = 0; t < gx * gy; ++t) {
+        const int tx = t % gx, ty = t / gx;
+        const uint32_t r0 = ranges[2 * t], r1 = ranges[2 * t + 1];
+        for (int ly = 0; ly < TILE; ++ly)
+            for (int lx = 0; lx < TILE; ++lx) {
+                const int x = tx * TILE + lx, y = ty * TILE + ly;
+                if (x >= W || y >= H) continue;
+                float T = 1.0f;
+                for (uint32_t j = r0; j < r1; ++j) {
+                    ++walked;
+                    const uint32_t g = point_list[j];
+                    const float* co = conic_opacity + 4 * (size_t)g;
+                    float dx, dy;
+                    float power = splat_power(means2D[2 * g], means2D[2 * g + 1], (float)x, (float)y, co[0], co[1], co[2], &dx, &dy);
+                    if (power > 0.0f) continue;
+                    ++evals;
+                    float alpha = fminf(0.99f, co[3] * expf(power));
+                    if (alpha < 1.0f / 255.0f) continue;
+                    float test_T = T * (1.0f - alpha);
+                    if (test_T < 0.0001f) break;
+                    T = test_T;
+                    ++contrib;
+                }
+            }
+    }
+    counts[0] = walked;
+    counts[1] = evals;
+    counts[2] = contrib;
+}
+
 void orc_blend_forward(int W, int H, const uint32_t* ranges, const uint32_t* point_list, const float* means2D,
                        const float* colors, const float* conic_opacity, const float* bg, float* out_color,
                        float* final_T, uint32_t* n_contrib, uint8_t* fragile) {

@@ -114,3 +114,35 @@ def test_oracle_against_reference_golden(path):
             ref = z[k].astype(np.float64)
             err = np.abs(g[k].astype(np.float64).reshape(ref.shape) - ref).max()
             assert err <= 2e-4 * max(np.abs(ref).max(), 1e-12), (k, err)
+
+
+def test_pair_counts_match_a_python_recount():
+    """orc_blend_pair_counts (the pairs/s figure of bench.py) against a plain-Python walk of the same lists."""
+    sc = scenes.head_scene(P=80, W=24, H=20, scale_mult=30.0, seed=9)
+    o = oracle_forward(orc, sc)
+    got = orc.pair_counts(o)
+    walked = evals = contrib = 0
+    gx = 2
+    for y in range(20):
+        for x in range(24):
+            a, b = o["ranges"][(y // 16) * gx + x // 16]
+            T = np.float32(1.0)
+            for j in range(int(a), int(b)):
+                walked += 1
+                g = o["point_list"][j]
+                co, m = o["conic_opacity"][g], o["means2D"][g]
+                dx, dy = np.float32(m[0] - x), np.float32(m[1] - y)
+                power = np.float32(-0.5) * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy
+                if power > 0:
+                    continue
+                evals += 1
+                alpha = min(np.float32(0.99), np.float32(co[3] * np.exp(power)))
+                if alpha < np.float32(1.0 / 255.0):
+                    continue
+                test_T = np.float32(T * (np.float32(1.0) - alpha))
+                if test_T < np.float32(0.0001):
+                    break
+                T = test_T
+                contrib += 1
+    assert got["walked"] == walked and abs(got["exp_evaluated"] - evals) <= 2 and abs(got["contributing"] - contrib) <= 2
+    assert got["contributing"] <= got["exp_evaluated"] <= got["walked"] <= int((o["ranges"][:, 1] - o["ranges"][:, 0]).max()) * 24 * 20
