@@ -279,3 +279,44 @@ def test_expand_factors_kernel_and_single_rank_identity(cuda_device):
     flame.flame_backward_raw(t("betas"), m["J_regressor"], m["parents"], m["lbs_weights"], r["workspace"], up, (200, 400),
                              l0=300, want=(False, False, False), record=rec2[0])
     assert torch.equal(rec2, record)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_LBS), reason="reference tree not mounted")
+def test_reference_FLAME_methods_run_on_cpu_and_match_the_oracle(monkeypatch):
+    """flame/FLAME.py's own `forward_with_delta_blendshape` and `forward` (the two calls of model/fateavatar.py:211-222),
+    executed unchanged on an instance whose buffers are the synthetic model (the constructor needs the licensed FLAME
+    pickle, so it is bypassed), against the oracle's restatement of those methods."""
+    import sys
+
+    pkg = types.ModuleType("flame")
+    pkg.__path__ = ["/root/reference/flame"]
+    monkeypatch.setitem(sys.modules, "flame", pkg)
+    for name in ("lbs", "FLAME"):
+        spec = importlib.util.spec_from_file_location(f"flame.{name}", f"/root/reference/flame/{name}.py")
+        mod = importlib.util.module_from_spec(spec)
+        monkeypatch.setitem(sys.modules, f"flame.{name}", mod)
+        spec.loader.exec_module(mod)
+    FLAME = sys.modules["flame.FLAME"].FLAME
+    f = scenes.flame_inputs(seed=17, V=70)
+    obj = FLAME.__new__(FLAME)
+    torch.nn.Module.__init__(obj)
+    obj.dtype, obj.n_shape, obj.n_exp = torch.float64, f["n_shape"], f["n_exp"]
+    t = lambda k: torch.from_numpy(f[k]).double()
+    for k in ("v_template", "shapedirs", "posedirs", "J_regressor", "lbs_weights"):
+        obj.register_buffer(k, t(k))
+    obj.register_buffer("parents", torch.from_numpy(f["parents"]))
+    expr, pose = t("betas")[None, 300:], t("pose")[None]
+    deltas = {k: t(k).requires_grad_(True) for k in DELTAS}
+    v_ref, pf_ref, A_ref = obj.forward_with_delta_blendshape(expr, pose, deltas["delta_shapedirs"], deltas["delta_posedirs"],
+                                                             deltas["delta_vertex"])
+    vo_ref, _, Ao_ref = FLAME.forward(obj, expr, pose)
+    g = np.random.default_rng(3).standard_normal((70, 3))
+    (v_ref[0] * torch.from_numpy(g)).sum().backward()
+    o, o0 = oracle_run(f, upstream=g), oracle_run(f, deltas=False)
+    assert v_ref.shape == (1, 70, 3) and pf_ref.shape == (1, 36) and A_ref.shape == (1, 5, 4, 4)
+    np.testing.assert_allclose(o["verts"], v_ref[0].detach().numpy(), rtol=0, atol=1e-13)
+    np.testing.assert_allclose(o["A"], A_ref[0].detach().numpy(), rtol=0, atol=1e-13)
+    np.testing.assert_allclose(o0["verts"], vo_ref[0].numpy(), rtol=0, atol=1e-13)
+    np.testing.assert_allclose(o0["A"], Ao_ref[0].numpy(), rtol=0, atol=1e-13)
+    for k in DELTAS:
+        np.testing.assert_allclose(o["grads"][k], deltas[k].grad.numpy(), rtol=0, atol=1e-12 * max(1.0, float(deltas[k].grad.abs().max())))

@@ -142,3 +142,8 @@ def test_oracle_mesh_functions_match_golden_fixture_from_reference():
     _, canon = po.compute_face_orientation(torch.from_numpy(p["canon_verts"])[None], faces)
     assert np.array_equal(orient[0, ::7].numpy(), gold["orient"]) and np.array_equal(scale[0, ::7].numpy(), gold["scale"])
     assert np.array_equal(normals[0, ::7].numpy(), gold["normals"]) and np.array_equal(canon[0, ::7].numpy(), gold["canon_scale"])
+    # barycentric positions (mesh_sampling.py:171-200): the oracle's xyz with a zero shell offset
+    t = lambda k: torch.from_numpy(p[k])
+    xyz, _, _, _ = po.pose_splats(verts[0], faces, t("face_index"), t("bary"), canon[0], t("scaling_raw"), t("rotation_raw"),
+                                  torch.zeros_like(t("offset_raw")), t("opacity_raw"), shell_len=p["shell_len"])
+    assert np.array_equal(xyz.numpy(), gold["pos"])

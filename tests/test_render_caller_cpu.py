@@ -80,3 +80,58 @@ def test_cpu_dropin_keeps_the_reference_argument_checks_and_config1_runs():
         r(x, x, torch.ones(4, 1), scales=torch.ones(4, 3), rotations=torch.ones(4, 4))
     with pytest.raises(Exception, match="scale/rotation pair"):
         r(x, x, torch.ones(4, 1), shs=torch.zeros(4, 1, 3))
+
+
+REF_ROOT = "/root/reference"
+
+
+def _load(name, path, monkeypatch):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    monkeypatch.setitem(sys.modules, name, mod)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.skipif(not os.path.exists(REF_RENDER), reason="reference tree not mounted")
+def test_reference_gaussian_model_and_render_on_cpu_match_pose_stage_activations(monkeypatch):
+    """The reference's own GaussianModel (volume_rendering/gaussian_model.py:105-128 getters) filled the way
+    FateAvatar.forward fills it (model/fateavatar.py:244-258) and rendered by its own render(): equals this repo's
+    SplatCloud + render on the same raw parameters.  plyfile and the CUDA knn extension are stubbed -- they are imported
+    by that file but not used on this path."""
+    import types
+
+    stub_ply = types.ModuleType("plyfile")
+    stub_ply.PlyData = stub_ply.PlyElement = object
+    monkeypatch.setitem(sys.modules, "plyfile", stub_ply)
+    knn_pkg, knn_c = types.ModuleType("simple_knn"), types.ModuleType("simple_knn._C")
+    knn_c.distCUDA2 = lambda pts: torch.from_numpy(orc.knn_mean_dist2(pts.detach().cpu().numpy()))
+    monkeypatch.setitem(sys.modules, "simple_knn", knn_pkg)
+    monkeypatch.setitem(sys.modules, "simple_knn._C", knn_c)
+    for pkg in ("tools", "tools.gs_utils"):  # the reference's package names, loaded from its files by path
+        m = types.ModuleType(pkg)
+        m.__path__ = []
+        monkeypatch.setitem(sys.modules, pkg, m)
+    for mod in ("general_utils", "system_utils", "sh_utils", "graphics_utils"):
+        _load(f"tools.gs_utils.{mod}", f"{REF_ROOT}/tools/gs_utils/{mod}.py", monkeypatch)
+    monkeypatch.setitem(sys.modules, "diff_gaussian_rasterization", cpu_dropin)
+    gm = _load("ref_gaussian_model_cpu", f"{REF_ROOT}/volume_rendering/gaussian_model.py", monkeypatch)
+    ref = _load("ref_render_3dgs_cpu2", REF_RENDER, monkeypatch)
+
+    sc = scenes.head_scene(P=1200, W=80, H=64, sh_degree=0, scale_mult=8.0, seed=31)
+    cam, cloud = _camera_and_cloud(sc)
+    gaussian = gm.GaussianModel(sh_degree=0)
+    leaf = lambda t: t.detach().clone().requires_grad_(True)
+    gaussian._xyz, gaussian._features_dc = leaf(cloud._xyz), leaf(cloud._features)
+    gaussian._features_rest = torch.zeros(1200, 0, 3)
+    gaussian._scaling, gaussian._rotation, gaussian._opacity = leaf(cloud._scaling), leaf(cloud._rotation), leaf(cloud._opacity)
+    bg = torch.from_numpy(sc["bg"])
+    out_ref = ref.render(cam, gaussian, bg, device="cpu")
+    out_new = rmod.render(cam, cloud, bg, device="cpu", rasterizer_module=cpu_dropin)
+    assert torch.equal(out_ref["render"], out_new["render"]) and torch.equal(out_ref["radii"], out_new["radii"])
+    g = torch.from_numpy(np.random.default_rng(1).standard_normal((3, 64, 80)).astype(np.float32))
+    (out_ref["render"] * g).sum().backward()
+    (out_new["render"] * g).sum().backward()
+    for a, b in ((gaussian._xyz, cloud._xyz), (gaussian._features_dc, cloud._features), (gaussian._scaling, cloud._scaling),
+                 (gaussian._rotation, cloud._rotation), (gaussian._opacity, cloud._opacity)):
+        assert torch.equal(a.grad, b.grad)
