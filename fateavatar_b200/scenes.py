@@ -256,3 +256,22 @@ def flame_inputs(seed=0, V=None, n_shape=300, n_exp=100, J=5, with_deltas=True):
     out = _f32(out)
     out["parents"] = parents
     return out
+
+
+def small_avatar(seed=0, n_lat=9, n_lon=16, N=900):
+    """A complete miniature avatar for whole-frame tests: FLAME-shaped model on a small ellipsoid mesh (V = (n_lat-1) *
+    n_lon + 2 vertices), N splat sites on it and raw splat parameters sized for a 64x80 render at distance 1.25."""
+    rng = np.random.default_rng(seed)
+    verts, faces = ellipsoid_mesh(n_lat=n_lat, n_lon=n_lon)
+    f = flame_inputs(seed=seed, V=verts.shape[0])
+    f["v_template"] = (verts - verts.mean(0, keepdims=True)).astype(np.float32)
+    tri = verts[faces]
+    area = 0.5 * np.linalg.norm(np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]), axis=1).astype(np.float64)
+    f.update(
+        faces=faces, face_index=rng.choice(faces.shape[0], size=N, p=area / area.sum()).astype(np.int64),
+        bary=rng.dirichlet(np.ones(3), N).astype(np.float32),
+        scaling_raw=(np.log(6e-3) + 0.3 * rng.standard_normal((N, 3))).astype(np.float32),
+        rotation_raw=(np.array([1, 0, 0, 0], np.float32) + 0.5 * rng.standard_normal((N, 4))).astype(np.float32),
+        offset_raw=(0.5 * rng.standard_normal((N, 1))).astype(np.float32), opacity_raw=rng.standard_normal((N, 1)).astype(np.float32),
+        features_dc=((rng.uniform(0, 1, (N, 1, 3)) - 0.5) / SH_C0).astype(np.float32), shell_len=0.05)
+    return f

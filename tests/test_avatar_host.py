@@ -119,3 +119,91 @@ def test_forward_frame_and_attach_equal_the_separate_operators(cuda_device):
     assert torch.equal(out["verts"], verts) and torch.equal(out["verts_orig"], verts_orig)
     assert float((out["rgb_image"][0].detach() - img.detach()).abs().max()) <= 1e-4  # camera matrices differ in the last fp32 bit
     assert float((out["radii"][0] != radii).float().mean()) <= 1e-3
+
+
+REF = "/root/reference"
+GOLDEN_FRAME = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frame_small.npz")
+FRAME_CASE = dict(seed=51, n_lat=9, n_lon=16, N=900)   # tests/golden/make_frame_golden.py
+FRAME_RES = (64, 80)
+
+
+def oracle_frame(a, inp, leaves):
+    """This repo's oracle composition of one frame on the CPU (what the fused GPU path is tested against):
+    FrameCamera + flame_oracle + pose_oracle.pose_splats + the C oracle rasterizer behind the operator API."""
+    from oracle import cpu_dropin, flame_oracle as fo, pose_oracle as po
+
+    t = lambda x: torch.from_numpy(np.asarray(x))
+    fm = {k: t(a[k]) for k in ("v_template", "shapedirs", "posedirs", "J_regressor", "lbs_weights")}
+    fm["parents"] = t(a["parents"])
+    faces = t(a["faces"])
+    _, canon = po.compute_face_orientation(fm["v_template"], faces)
+    betas = torch.cat([torch.zeros(a["n_shape"]), inp["expression"][0]])
+    verts, _, _ = fo.forward_with_delta_blendshape(fm, betas, inp["flame_pose"][0], leaves["delta_shapedirs"],
+                                                   leaves["delta_posedirs"], leaves["delta_vertex"])
+    verts_orig, _, _ = fo.forward_with_delta_blendshape(fm, betas, inp["flame_pose"][0])
+    xyz, sc, ro, op = po.pose_splats(verts, faces, t(a["face_index"]), t(a["bary"]), canon, leaves["_scaling"], leaves["_rotation"],
+                                     leaves["_offset"], leaves["_opacity"], shell_len=a["shell_len"])
+    fx, fy = float(inp["fovx"][0]), float(inp["fovy"][0])
+    cam = avatar.FrameCamera(inp["cam_pose"][:, :3, :3], inp["cam_pose"][:, :3, 3], fx, fy, FRAME_RES)
+    rs = cpu_dropin.GaussianRasterizationSettings(FRAME_RES[0], FRAME_RES[1], math.tan(fx / 2), math.tan(fy / 2), torch.ones(3), 1.0,
+                                                  cam.world_view_transform, cam.full_proj_transform, 0, cam.camera_center,
+                                                  False, False)
+    img, radii = cpu_dropin.GaussianRasterizer(rs)(means3D=xyz, means2D=torch.zeros_like(xyz), shs=leaves["_features_dc"],
+                                                   opacities=op, scales=sc, rotations=ro)
+    return img, radii, verts, verts_orig
+
+
+@pytest.mark.skipif(not os.path.exists(f"{REF}/model/fateavatar.py"), reason="reference tree not mounted")
+def test_reference_FateAvatar_forward_runs_on_cpu_and_matches_the_oracle_composition(monkeypatch):
+    """The reference's UNCHANGED `FateAvatar.forward` (model/fateavatar.py:196-298) executed on the CPU through
+    tests/ref_frame_harness.py must equal the composition this repo uses as oracle for the fused path (FrameCamera +
+    flame_oracle + pose_oracle.pose_splats + rasterizer oracle): image, meshes, radii and every parameter gradient."""
+    import ref_frame_harness as H
+
+    FateAvatar, FLAME, mesh_compute = H.load_reference(monkeypatch)
+    a = scenes.small_avatar(**FRAME_CASE)
+    ref = H.build_reference_model(FateAvatar, FLAME, mesh_compute, a, FRAME_RES)
+    inp = H.frame_input(a)
+    out = FateAvatar.forward(ref, inp)                                     # <- the reference's own code
+    assert out["rgb_image"].shape == (1, 3) + FRAME_RES and out["bs"] == 1 and int((out["radii"][0] > 0).sum()) > 500
+    leaves = {n: getattr(ref, n) for n in H.PARAMS}
+    img, radii, verts, verts_orig = oracle_frame(a, inp, leaves)
+    # measured: image 2.4e-6, meshes 3e-8, radii identical, gradients <= 1e-5 (the reference inverts its camera twice)
+    assert float((out["verts"][0] - verts).abs().max()) <= 1e-6 and float((out["verts_orig"][0] - verts_orig).abs().max()) <= 1e-6
+    assert float((out["rgb_image"][0] - img).abs().max()) <= 2e-5
+    assert float((out["radii"][0] != radii).float().mean()) <= 1e-3
+    assert torch.equal(out["visibility_filter"][0], out["radii"][0] > 0)
+    assert torch.equal(out["scale"], torch.exp(ref._scaling))
+    assert torch.equal(out["raw_rot"], avatar.quaternion_to_axis_angle(ref._rotation))
+    w = torch.from_numpy(np.random.default_rng(2).standard_normal((3,) + FRAME_RES).astype(np.float32))
+    (out["rgb_image"][0] * w).sum().backward()
+    g_ref = {n: getattr(ref, n).grad.clone() for n in H.PARAMS}
+    for n in H.PARAMS:
+        getattr(ref, n).grad = None
+    (img * w).sum().backward()
+    for n in H.PARAMS:
+        a_, b_ = getattr(ref, n).grad, g_ref[n]
+        assert float((a_ - b_).abs().max()) <= 1e-4 * max(float(b_.abs().max()), 1e-12), n
+
+
+def test_oracle_frame_matches_golden_from_the_reference_forward():
+    """tests/golden/frame_small.npz holds what the reference's own FateAvatar.forward produced (make_frame_golden.py)."""
+    import ref_frame_harness as H
+
+    gold = np.load(GOLDEN_FRAME)
+    a = scenes.small_avatar(**FRAME_CASE)
+    t = lambda x: torch.from_numpy(np.asarray(x))
+    keys = dict(_scaling="scaling_raw", _rotation="rotation_raw", _offset="offset_raw", _opacity="opacity_raw", _features_dc="features_dc",
+                delta_vertex="delta_vertex", delta_posedirs="delta_posedirs", delta_shapedirs="delta_shapedirs")
+    leaves = {n: t(a[k]).clone().requires_grad_(True) for n, k in keys.items()}
+    img, radii, verts, verts_orig = oracle_frame(a, H.frame_input(a), leaves)
+    assert np.abs(img.detach().numpy() - gold["rgb_image"]).max() <= 2e-5 and np.abs(verts.detach().numpy() - gold["verts"]).max() <= 1e-6
+    assert (radii.numpy() != gold["radii"]).mean() <= 1e-3
+    w = torch.from_numpy(np.random.default_rng(2).standard_normal((3,) + FRAME_RES).astype(np.float32))
+    (img * w).sum().backward()
+    for n in H.PARAMS:
+        g, want = leaves[n].grad.numpy(), gold["grad" + n]
+        if n == "delta_shapedirs":
+            assert not g[:, :, :300].any()
+            g = g[:, :, 300:]
+        assert np.abs(g - want).max() <= 1e-4 * max(np.abs(want).max(), 1e-12), n

@@ -16,7 +16,7 @@ import torch
 from fateavatar_b200 import _lib, knn, rasterizer as R, render as rmod, scenes
 from oracle import oracle as orc
 from oracle import ref_loader
-from util import GRAD_NAMES, assert_grad_close, oracle_forward, settings
+from util import rasterizer_goldens, GRAD_NAMES, assert_grad_close, oracle_forward, settings
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -195,7 +195,7 @@ def test_autograd_through_render_mirror(cuda_device):
     assert np.array_equal(out["radii"].cpu().numpy(), o["radii"])
 
 
-@pytest.mark.parametrize("path", sorted(p for p in glob.glob(os.path.join(HERE, "golden", "*.npz")) if not os.path.basename(p).startswith(("flame", "pose"))) or [None])
+@pytest.mark.parametrize("path", rasterizer_goldens(HERE) or [None])
 def test_against_reference_golden(path, cuda_device):
     if path is None:
         pytest.skip("no golden fixtures committed yet")

@@ -7,7 +7,7 @@ import pytest
 
 from fateavatar_b200 import scenes
 from oracle import oracle as orc
-from util import oracle_forward
+from util import rasterizer_goldens, oracle_forward
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -83,7 +83,7 @@ def test_oracle_mark_visible_and_knn():
     assert np.allclose(small, np.sort(d2, axis=1)[:, :3].mean(1), rtol=1e-5)
 
 
-GOLDEN = sorted(p for p in glob.glob(os.path.join(HERE, "golden", "*.npz")) if not os.path.basename(p).startswith(("flame", "pose")))
+GOLDEN = rasterizer_goldens(HERE)
 
 
 @pytest.mark.parametrize("path", GOLDEN or [None])

@@ -27,3 +27,17 @@ def assert_grad_close(name, got, ref, rtol=2e-4):
     scale = max(float(np.abs(ref).max()), 1e-12) if ref.size else 1.0
     err = float(np.abs(got - ref).max()) if ref.size else 0.0
     assert err <= rtol * scale, f"{name}: max abs err {err:.3e} > {rtol:.0e} * {scale:.3e}"
+
+
+def rasterizer_goldens(here):
+    """The golden fixtures of the rasterizer (tests/golden/make_golden.py): the .npz files that carry a `scene` key.
+    Other stages keep their own fixtures in the same directory (flame_*, pose_*, frame_*)."""
+    import glob
+    import os
+
+    out = []
+    for path in sorted(glob.glob(os.path.join(here, "golden", "*.npz"))):
+        with np.load(path) as z:
+            if "scene" in z.files:
+                out.append(path)
+    return out
