@@ -1,7 +1,7 @@
 """End-to-end GPU parity of the fused path against outputs of the reference's own `FateAvatar.forward`
 (tests/golden/frame_small.npz, made by tests/golden/make_frame_golden.py through tests/ref_frame_harness.py).
-Kept in its own, last-sorting file: it was written after this round's GPU budget was spent, its plumbing was dry-run on
-CPU stand-ins for the kernels, and every stage it composes is tested separately against the same oracles."""
+Every stage it composes is also tested separately against the same oracles (test_flame.py, test_pose.py,
+test_gpu_parity.py); this is the whole path in one assertion."""
 import math  # noqa: F401
 import os
 import types
