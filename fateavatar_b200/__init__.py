@@ -30,7 +30,7 @@ def install():
         sys.path.insert(0, _DROPIN)
     for name in ("diff_gaussian_rasterization", "simple_knn", "simple_knn._C"):
         mod = sys.modules.get(name)
-        if mod is not None and not getattr(mod, "__file__", "").startswith(_DROPIN):
+        if mod is not None and not (getattr(mod, "__file__", None) or "").startswith(_DROPIN):
             del sys.modules[name]
     import diff_gaussian_rasterization  # noqa: F401
     import simple_knn._C  # noqa: F401

@@ -54,8 +54,8 @@ class GaussianRasterizationSettings(NamedTuple):
 # ---- workspace / capacity bookkeeping ---------------------------------------------------------------------
 
 _ASYNC = os.environ.get("FATESPLAT_ASYNC", "0") == "1"
-_capacity_hint = {}   # (device index, W, H) -> instances seen recently
-_tile_hint = {}       # (device index, W, H) -> heaviest tile seen recently (fs_set_tile_hint)
+_capacity_hint = {}   # (device index, W, H, P) -> instances seen recently
+_tile_hint = {}       # (device index, W, H, P) -> heaviest tile seen recently (fs_set_tile_hint)
 _pinned = {}          # device index -> (pinned uint8 tensor viewed as FsFrameInfo slots, next slot, events)
 _N_SLOTS = 64
 _INFO_BYTES = C.sizeof(FsFrameInfo)
@@ -88,10 +88,68 @@ def _slot_info(ent, slot):
     return FsFrameInfo.from_address(ent["buf"].data_ptr() + slot * _INFO_BYTES)
 
 
-def _initial_capacity(P, W, H, dev):
-    hint = _capacity_hint.get((dev, W, H), 0)
-    cap = max(8 * P + 65536, int(hint * 1.5) + 4096)
+def _initial_capacity(P, key):
+    """Instance capacity of the next frame: 1.5x the largest recent frame of this (device, W, H, P) once one has been
+    seen (the reference sizes its binning buffers from the exact count, rasterizer_impl.cu:281-287; an overflow here
+    is flagged and the frame re-run, never silent), 8 instances per splat for the very first frame."""
+    hint = _capacity_hint.get(key, 0)
+    cap = int(hint * 1.5) + 4096 if hint else 8 * P + 65536
     return (cap + 1023) // 1024 * 1024
+
+
+# ---- persistent workspace arena ---------------------------------------------------------------------------
+# The reference allocates its three scratch buffers inside every call (rasterize_points.cu:68-78, resized through
+# std::function callbacks).  Here a frame makes no allocator call at all: workspaces come from a grow-only pool per
+# (device, stream).  A slot is handed out as a view of its backing tensor and counts as busy for as long as ANY
+# tensor shares its storage -- the state returned by forward_raw, autograd's saved tensors, decode_workspace views --
+# so it returns to the pool by itself when the last of them is dropped (after the backward, normally).
+_arena = {}          # (device index, raw stream) -> list of uint8 backing tensors
+_ARENA_MAX_SLOTS = 64
+arena_stats = {"hits": 0, "allocs": 0}
+
+
+def _storage_users(t):
+    return torch._C._storage_Use_Count(t.untyped_storage()._cdata)
+
+
+def _arena_get(nbytes, dev, di, stream_ptr):
+    slots = _arena.setdefault((di, stream_ptr), [])
+    small = -1
+    for k, (t, idle) in enumerate(slots):
+        if _storage_users(t) <= idle:
+            if t.numel() >= nbytes:
+                arena_stats["hits"] += 1
+                return t[:nbytes] if t.numel() != nbytes else t.view(-1)
+            small = k
+    arena_stats["allocs"] += 1
+    t = torch.empty(max(nbytes, 0) if small < 0 else max(nbytes, int(slots[small][0].numel() * 1.25)), dtype=torch.uint8,
+                    device=dev)
+    ent = (t, _storage_users(t))
+    if small >= 0:
+        slots[small] = ent  # grow-only: the undersized free slot is replaced
+    elif len(slots) < _ARENA_MAX_SLOTS:
+        slots.append(ent)
+    return t[:nbytes] if t.numel() != nbytes else t.view(-1)
+
+
+def trim_workspace_arena():
+    """Drop every idle workspace slot (e.g. after densification changed P for good)."""
+    for key, slots in _arena.items():
+        slots[:] = [(t, idle) for t, idle in slots if _storage_users(t) > idle]
+
+
+def _capacity_for_bytes(lib, P, W, H, ws):
+    """Largest instance capacity whose layout fits the caller-provided workspace tensor."""
+    if not (ws.is_cuda and ws.dtype == torch.uint8 and ws.is_contiguous()):
+        raise FateSplatError("workspace= must be a contiguous uint8 CUDA tensor")
+    base, n = lib.fs_workspace_bytes(P, W, H, 0), ws.numel()
+    per = (lib.fs_workspace_bytes(P, W, H, 1 << 20) - base) / float(1 << 20)  # bytes per instance, incl. checkpoints
+    cap = int(max(0, n - base - 65536) / per) // 1024 * 1024
+    while cap > 0 and lib.fs_workspace_bytes(P, W, H, cap) > n:
+        cap -= 1024
+    if cap <= 0:
+        raise FateSplatError(f"workspace= of {n} bytes is too small for P={P}, {W}x{H}")
+    return cap
 
 
 def _drain_pending(ent, dev, block=False):
@@ -149,10 +207,12 @@ def _prep(t, name, dev):
     return t.contiguous()
 
 
-def forward_raw(raster_settings, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp):
+def forward_raw(raster_settings, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                workspace=None):
     """One fs_forward call.  Returns (color, radii, state) where `state` carries the workspace the backward and
     the parity taps need.  This is the C-ABI path with device-resident tensors; the autograd Function and
-    bench.py both go through it."""
+    bench.py both go through it.  The workspace comes from the persistent arena (no allocator call per frame) unless
+    the caller passes its own uint8 CUDA tensor as `workspace=` (then its size fixes the instance capacity)."""
     lib = _lib.load()
     if means3D.ndim != 2 or means3D.shape[1] != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:57-59
@@ -181,27 +241,32 @@ def forward_raw(raster_settings, means3D, sh, colors_precomp, opacities, scales,
     radii = torch.zeros((P,), dtype=torch.int32, device=dev) if P == 0 else \
         torch.empty((P,), dtype=torch.int32, device=dev)
     num_rendered = 0
+    own_ws = workspace
     workspace = torch.empty(0, dtype=torch.uint8, device=dev)
     capacity = 0
     launches = 0
     if P != 0:
         di = dev.index if dev.index is not None else torch.cuda.current_device()
-        key = (di, W, H)
+        key = (di, W, H, P)
         ent = _pinned_slots(di)
         with _lib.on_device(dev):
             stream_ptr = _lib.stream_ptr(dev)
             capturing = torch.cuda.is_current_stream_capturing()
             if _ASYNC and not capturing:
                 _drain_pending(ent, di)
-            capacity = _initial_capacity(P, W, H, di)
+            capacity = _initial_capacity(P, key)
+            if own_ws is not None:
+                capacity = _capacity_for_bytes(lib, P, W, H, own_ws)
             lib.fs_set_tile_hint(int(_tile_hint.get(key, 0) * 1.25))
             while capturing:
                 # CUDA-graph capture (fateavatar_b200.graph): the launches are recorded, not run, so nothing can be
                 # waited for.  The frame gets a generous fixed capacity and its own pinned header, which every
                 # replay refreshes; CapturedStep.check() reads it after a replay and raises on overflow.
-                capacity = max(capacity, (2 * int(_capacity_hint.get(key, 0)) + 1023) // 1024 * 1024)
+                if own_ws is None:
+                    capacity = max(capacity, (2 * int(_capacity_hint.get(key, 0)) + 1023) // 1024 * 1024)
                 nbytes = lib.fs_workspace_bytes(P, W, H, capacity)
-                workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                # graph-private memory: allocated once at capture time, replays make no allocator call
+                workspace = own_ws if own_ws is not None else torch.empty(nbytes, dtype=torch.uint8, device=dev)
                 if not _capture_header_pool:
                     raise FateSplatError("CUDA-graph capture needs pinned headers reserved beforehand "
                                          "(use fateavatar_b200.graph.CapturedStep, or reserve_capture_headers())")
@@ -218,7 +283,7 @@ def forward_raw(raster_settings, means3D, sh, colors_precomp, opacities, scales,
                 break
             while not capturing:
                 nbytes = lib.fs_workspace_bytes(P, W, H, capacity)
-                workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                workspace = own_ws if own_ws is not None else _arena_get(nbytes, dev, di, stream_ptr)
                 slot = ent["next"]
                 ent["next"] = (slot + 1) % _N_SLOTS
                 if _ASYNC and any(p[0] == slot for p in ent["pending"]):
@@ -245,7 +310,11 @@ def forward_raw(raster_settings, means3D, sh, colors_precomp, opacities, scales,
                 _tile_hint[key] = max(int(info.max_tile_instances), int(_tile_hint.get(key, 0) * 0.9))
                 if not info.overflow:
                     break
+                if own_ws is not None:
+                    raise FateSplatError(f"the caller's workspace holds {capacity} instances but the frame has "
+                                         f"{num_rendered}: pass a larger one (fs_workspace_bytes)")
                 capacity = (int(num_rendered * 1.25) + 1023) // 1024 * 1024  # re-run, exact results
+                del workspace  # the undersized slot goes back to the arena before the larger one is taken
         if rs.debug:
             torch.cuda.synchronize(dev)  # surfaces asynchronous CUDA errors like CHECK_CUDA(debug)
     empty = torch.empty(0, device=dev)
@@ -357,10 +426,13 @@ class GaussianRasterizer(nn.Module):
             P = pos.shape[0]
             present = torch.zeros((P,), dtype=torch.uint8, device=pos.device)
             if P:
+                view = _prep(rs.viewmatrix, "viewmatrix", pos.device)
+                proj = _prep(rs.projmatrix, "projmatrix", pos.device)
+                if view is None or proj is None or view.numel() != 16 or proj.numel() != 16:
+                    raise FateSplatError("markVisible needs 4x4 viewmatrix / projmatrix in the raster settings")
                 with _lib.on_device(pos.device):
-                    rc = _lib.load().fs_mark_visible(P, pos.data_ptr(), rs.viewmatrix.contiguous().data_ptr(),
-                                                     rs.projmatrix.contiguous().data_ptr(), present.data_ptr(),
-                                                     _lib.stream_ptr(pos.device))
+                    rc = _lib.load().fs_mark_visible(P, pos.data_ptr(), view.data_ptr(), proj.data_ptr(),
+                                                     present.data_ptr(), _lib.stream_ptr(pos.device))
                     _lib.check(rc, "fs_mark_visible")
             return present.bool()
 
