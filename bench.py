@@ -74,13 +74,22 @@ FLAME_KEYS = ("v_template", "shapedirs", "posedirs", "J_regressor", "lbs_weights
 DELTA_KEYS = ("delta_vertex", "delta_shapedirs", "delta_posedirs")
 
 
-def make_frames(args, n, seed0=0):
-    """n frames of one avatar: shared splat parameters / splat sites and FLAME-shaped model (the model), per-frame
-    expression + pose coefficients (what the dataset supplies, train/dataset.py)."""
+_BASE = {}
+
+
+def make_frames(args, n, rank=0):
+    """n frames of rank `rank`'s shard of one avatar: shared splat parameters / splat sites and FLAME-shaped model (the
+    model, identical on every rank), per-frame expression + pose coefficients (what the dataset supplies,
+    train/dataset.py)."""
     import numpy as np
 
     from fateavatar_b200 import scenes
 
+    seed0 = 0
+    if args.P in _BASE:
+        base = _BASE[args.P]
+        return [dict(base, **{k: scenes.flame_inputs(seed=1000 + 100 * rank + i, V=8, with_deltas=False)[k]
+                              for k in ("betas", "pose")}) for i in range(n)]
     base = scenes.pose_inputs(N=args.P, seed=seed0)
     base.pop("verts")
     fl = scenes.flame_inputs(seed=seed0)  # same 5002-vertex template the splat sites were sampled on
@@ -90,13 +99,8 @@ def make_frames(args, n, seed0=0):
     base["shs"] = ((rng.uniform(0, 1, (args.P, 1, 3)) - 0.5) / scenes.SH_C0).astype(np.float32)
     base["bg"] = np.ones(3, np.float32)
     base["camera"] = scenes.make_camera(args.res, args.res, 0.35, 0.35, T=[0, 0, 1.25])
-    frames = []
-    for i in range(n):
-        f = dict(base)
-        fi = scenes.flame_inputs(seed=seed0 + 1000 + i, V=8, with_deltas=False)  # only this frame's coefficients
-        f["betas"], f["pose"] = fi["betas"], fi["pose"]
-        frames.append(f)
-    return frames
+    _BASE[args.P] = base
+    return make_frames(args, n, rank)
 
 
 def cpu_pose_and_render(f, dpix, orc, po, fo, torch):
@@ -237,10 +241,12 @@ def main():
         print(json.dumps(line), file=REAL_STDOUT, flush=True)
         return
 
+    import types
+
     import numpy as np
     import torch
 
-    from fateavatar_b200 import _lib, rasterizer as R, scenes
+    from fateavatar_b200 import _lib, avatar, flame, parallel, rasterizer as R
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl new needs a CUDA device (no CPU fallback exists)")
@@ -253,151 +259,138 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    # ---- inputs resident in HBM: each rank owns its own ring of frames (its shard of the video) -------------
-    from fateavatar_b200 import pose
-
-    frames = make_frames(args, N_RING, seed0=100 * rank)
+    # ---- the avatar (identical on every rank) and this rank's shard of the frames -----------------------------
+    frames = make_frames(args, N_RING, rank=rank)
     f0 = frames[0]
     P = args.P
-    cam = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in f0["camera"].items()}
     tdev = lambda a: torch.from_numpy(a).to(dev)
-    faces, fidx, bary = tdev(f0["faces"]), tdev(f0["face_index"]), tdev(f0["bary"])
-    params = [tdev(f0[k]) for k in ("scaling_raw", "rotation_raw", "offset_raw", "opacity_raw")]
-    shs, bg = tdev(f0["shs"]), tdev(f0["bg"])
+    par = lambda a: torch.nn.Parameter(tdev(a))
+    cam = {k: (tdev(v) if isinstance(v, np.ndarray) else v) for k, v in f0["camera"].items()}
+    faces = tdev(f0["faces"])
     e1c = tdev(f0["canon_verts"])
     v0c, v1c, v2c = e1c[faces[:, 0]], e1c[faces[:, 1]], e1c[faces[:, 2]]
     a0c = torch.nn.functional.normalize(v1c - v0c, dim=-1)
     a1c = torch.nn.functional.normalize(torch.cross(a0c, v2c - v0c, dim=-1), dim=-1)
     a2c = -torch.nn.functional.normalize(torch.cross(a1c, a0c, dim=-1), dim=-1)
     canon = (((v1c - v0c).norm(dim=-1) + (a2c * (v2c - v0c)).sum(-1).abs()) / 2).contiguous()  # fateavatar.py:84-85
-    fmodel = {k: tdev(f0[k]) for k in FLAME_KEYS}
-    fmodel["parents"] = f0["parents"]
-    fdelta = {k: tdev(f0[k]) for k in DELTA_KEYS}
-    betas, fpose = [tdev(f["betas"]) for f in frames], [tdev(f["pose"]) for f in frames]
     n_shape, V, L = f0["n_shape"], f0["v_template"].shape[0], f0["shapedirs"].shape[-1]
     NPF = (len(f0["parents"]) - 1) * 9
+    bg = tdev(f0["bg"])
+    # a FateAvatar look-alike: the attributes model/fateavatar.py keeps, driven through the package's mirrors of
+    # FateAvatar.forward (avatar.forward_frame) and of the raw operator chain (parallel.AbiFrame)
+    flame_mod = types.SimpleNamespace(n_shape=n_shape, n_exp=L - n_shape, parents=torch.tensor(f0["parents"]),
+                                      **{k: tdev(f0[k]) for k in FLAME_KEYS})
+    model = types.SimpleNamespace(
+        flame=flame_mod, faces=faces, face_index=tdev(f0["face_index"]), bary_coords=tdev(f0["bary"]),
+        face_scaling_canonical=canon, _scaling=par(f0["scaling_raw"]), _rotation=par(f0["rotation_raw"]),
+        _offset=par(f0["offset_raw"]), _opacity=par(f0["opacity_raw"]), _features_dc=par(f0["shs"]),
+        delta_shapedirs=par(f0["delta_shapedirs"]), delta_posedirs=par(f0["delta_posedirs"]),
+        delta_vertex=par(f0["delta_vertex"]), shell_len=f0["shell_len"], bg_color=bg, img_res=(args.res, args.res),
+        cfg_model=types.SimpleNamespace(delta_blendshape=True, delta_vertex=True, resize_scale=True))
     rs = R.GaussianRasterizationSettings(args.res, args.res, cam["tanfovx"], cam["tanfovy"], bg, 1.0, cam["viewmatrix"],
                                          cam["projmatrix"], 0, cam["campos"], False, False)
-    dpix = [torch.randn(3, args.res, args.res, device=dev) for _ in range(N_RING)]
-    # Gradient memory.  What data-parallel training exchanges lives in ONE flat bucket, written in
-    # place by the kernels (no pack copy) and reduced by ONE collective per step:
-    #   [ splat parameter grads: scaling 3, rotation 4, offset 1, opacity 1 | SH 3 | screen-space statistic 3 ] x P
-    #   [ world x factor record of the FLAME delta gradients ]   (each rank fills its own slot, the others are zero,
-    #     so the sum all-reduce doubles as the all-gather of the rank-1 factors)
-    # Intermediate gradients (dL/dxyz, dL/dscale, ... of the rasterizer, dL/dverts) stay in scratch tensors.
-    from fateavatar_b200 import flame
 
-    rec_n = flame.factor_record_floats(V, L, NPF)
-    n_bucket = 15 * P + world * rec_n
-    # bucket = [A: SH 3P, screen-space statistic 3P | B: scaling 3P, rotation 4P, offset P, opacity P | C: factors]
+    def frame_inputs(r, k):
+        """(betas, pose, upstream image gradient) of frame k of rank r's shard, on this device."""
+        f = make_frames(args, k + 1, rank=r)[k] if r != rank else frames[k]
+        g = torch.Generator(device=dev)
+        g.manual_seed(1234 + 100 * r + k)
+        return tdev(f["betas"]), tdev(f["pose"]), torch.randn(3, args.res, args.res, device=dev, generator=g)
+
     # Exchange (N > 1), FATESPLAT_BENCH_EXCHANGE:
-    #   p2p (default)  the bucket lives in symmetric peer-mapped memory (two buffers used alternately); one barrier
-    #                  + ONE kernel (fs_p2p_allreduce: multimem.ld_reduce through the NVLink switch, or unicast peer
-    #                  loads) gives every rank the sum -- no NCCL call in the step
-    #   nccl           one NCCL all-reduce over the bucket
-    #   overlap        three asynchronous NCCL all-reduces (A, B, C) overlapped with the backward (measured slower)
-    mode = os.environ.get("FATESPLAT_BENCH_EXCHANGE", "p2p") if dist is not None else "none"
-    sym = None
-    if mode == "p2p":
+    #   p2p (default)  parallel.ShardedStep: the gradient bucket lives in symmetric peer-mapped memory (two buffers used
+    #                  alternately) and ONE kernel per step (fs_p2p_exchange) barriers the ranks, sums the splat part
+    #                  over NVLink / NVSwitch and expands the gathered FLAME factor records -- no NCCL call in the step
+    #   nccl           the same bucket through one NCCL all-reduce + fs_flame_expand_grads (comparison)
+    mode = workload_config(args)["exchange"] if dist is not None else "none"
+    sharded = None
+    if mode in ("p2p", "none"):
         try:
-            from fateavatar_b200.exchange import SymmetricBucket
-
-            sym = SymmetricBucket(n_bucket, dev)
+            sharded = parallel.ShardedStep(model, device=dev)
         except Exception as ex:  # e.g. no peer access between the visible devices
+            if mode == "none":
+                raise
             mode = f"nccl (symmetric memory unavailable: {repr(ex)[:120]})"
-    buckets = [sym.local(0), sym.local(1)] if sym is not None else [torch.zeros(n_bucket, device=dev)] * 2
-    scratch = torch.zeros(11 * P, device=dev)
-    d_verts = torch.empty(V, 3, device=dev)
-
-    def views(bucket):
-        rv = dict(means3D=scratch[0:3 * P], scales=scratch[3 * P:6 * P], rotations=scratch[6 * P:10 * P],
-                  opacity=scratch[10 * P:11 * P], sh=bucket[0:3 * P], means2D=bucket[3 * P:6 * P])
-        pv = (d_verts, bucket[6 * P:9 * P].view(P, 3), bucket[9 * P:13 * P].view(P, 4),
-              bucket[13 * P:14 * P].view(P, 1), bucket[14 * P:15 * P].view(P, 1))
-        gathered = bucket[15 * P:15 * P + world * rec_n].view(world, rec_n)
-        return dict(rv=rv, pv=pv, a=bucket[:6 * P], b=bucket[6 * P:15 * P], c=bucket[15 * P:n_bucket], all=bucket[:n_bucket],
-                    gathered=gathered, record=gathered[rank], others=[gathered[r] for r in range(world) if r != rank])
-
-    bviews = [views(buckets[0]), views(buckets[1])]
+    lay = parallel.GradLayout(P, V, L, NPF)
+    rec_n = lay.rec_floats
+    nccl_bucket = torch.zeros(lay.n_splat + world * rec_n, device=dev) if sharded is None else None
     fgrads = [torch.empty(V, 3, device=dev), torch.empty(V, 3, L, device=dev), torch.empty(NPF, 3 * V, device=dev)]
-    pose_out = [(torch.empty(P, 3, device=dev), torch.empty(P, 3, device=dev), torch.empty(P, 4, device=dev),
-                 torch.empty(P, 1, device=dev)) for _ in range(N_RING)]
-    fl_out = [flame.flame_forward_raw(betas[k], fpose[k], fmodel["v_template"], fmodel["shapedirs"], fmodel["posedirs"],
-                                      fmodel["J_regressor"], fmodel["parents"], fmodel["lbs_weights"],
-                                      fdelta["delta_vertex"], fdelta["delta_shapedirs"], fdelta["delta_posedirs"],
-                                      l0=n_shape) for k in range(N_RING)]
+    abi = [parallel.AbiFrame(model, rs, *frame_inputs(rank, k)) for k in range(N_RING)]
 
-    R.set_async(True)  # no host synchronisation inside the step; overflow is checked after the timed region
-    ring = [None] * N_RING
-    launches = [0]
-
-    overlap = mode == "overlap"
-
-    tick = [0]  # steps issued so far: consecutive steps alternate between the two bucket buffers
-
-    def step(i):
-        k = i % N_RING
-        t_ = tick[0]
-        tick[0] += 1
-        bv = bviews[t_ & 1]
-        rv, pv, record = bv["rv"], bv["pv"], bv["record"]
-        fo_ = flame.flame_forward_raw(betas[k], fpose[k], fmodel["v_template"], fmodel["shapedirs"], fmodel["posedirs"],
-                                      fmodel["J_regressor"], fmodel["parents"], fmodel["lbs_weights"],
-                                      fdelta["delta_vertex"], fdelta["delta_shapedirs"], fdelta["delta_posedirs"],
-                                      l0=n_shape, out=fl_out[k])
-        verts_k = fo_["verts"]
-        xyz, sc, ro, op = pose.pose_forward_raw(verts_k, faces, fidx, bary, canon, *params, shell_len=f0["shell_len"],
-                                                out=pose_out[k])
-        color, radii, st = R.forward_raw(rs, xyz, shs, None, op, sc, ro, None)
-        R.backward_raw(st, dpix[k], out=rv)
-        exchange = dist is not None and not args.no_collective
-        wa = dist.all_reduce(bv["a"], async_op=True) if exchange and overlap else None
-        pose.pose_backward_raw(verts_k, faces, fidx, bary, canon, *params, scratch[0:3 * P].view(P, 3),
-                               scratch[3 * P:6 * P].view(P, 3), scratch[6 * P:10 * P].view(P, 4),
-                               scratch[10 * P:11 * P].view(P, 1), shell_len=f0["shell_len"], out=pv)
-        if not exchange:
-            flame.flame_backward_raw(betas[k], fmodel["J_regressor"], fmodel["parents"], fmodel["lbs_weights"],
-                                     fo_["workspace"], d_verts, (V, L), l0=n_shape, out=fgrads)
-        else:
-            wb = dist.all_reduce(bv["b"], async_op=True) if overlap else None
-            # the FLAME delta gradients are rank-1 per frame: exchange their factors (~120 KB per rank; every rank
-            # fills its own slot of part C, the others are zero, so the sum is the all-gather) and expand the sum
-            # locally instead of all-reducing 26 MB
-            if sym is None:  # (in p2p mode the sum never lands in the bucket, so the other slots stay zero)
-                for o_ in bv["others"]:
-                    o_.zero_()
-            flame.flame_backward_raw(betas[k], fmodel["J_regressor"], fmodel["parents"], fmodel["lbs_weights"],
-                                     fo_["workspace"], d_verts, (V, L), l0=n_shape, want=(False, False, False),
-                                     record=record)
-            if sym is not None:
-                summed = sym.all_reduce(t_, n_bucket)  # rank-local sum of every rank's bucket
-                gathered = summed[15 * P:15 * P + world * rec_n].view(world, rec_n)
-            else:
-                dist.all_reduce(bv["c"] if overlap else bv["all"])
-                gathered = bv["gathered"]
+    def step(i, frame=None):
+        """One step issued call by call from Python: frame i of the ring (forward + backward), then the exchange."""
+        fr = frame if frame is not None else abi[i % N_RING]
+        if sharded is not None:
+            fr.run(sharded.fill_views(i), record=sharded.record(i), dense=fgrads)
+            if not args.no_collective:
+                return sharded.exchange(i)
+            return None
+        views = lay.views(nccl_bucket[:lay.n_splat])
+        gathered = nccl_bucket[lay.n_splat:].view(world, rec_n)
+        for r in range(world):
+            if r != rank:
+                gathered[r].zero_()
+        fr.run(views, record=gathered[rank], dense=None)
+        if not args.no_collective:
+            dist.all_reduce(nccl_bucket)
             flame.expand_factors(gathered, V, L, NPF, l0=n_shape, out=fgrads)
-            if overlap:
-                wa.wait()
-                wb.wait()
-        ring[k] = st  # keeps N_RING workspaces alive => consecutive steps touch different memory
-        # 2 memset nodes (rasterizer) + 1 (pose backward) + 2 pose + 4 FLAME kernels
-        launches[0] = st["launches"] + st.get("launches_bwd", 0) + 2 + 2 + 1 + 4
-        return color
+        return dict(views, delta_vertex=fgrads[0], delta_shapedirs=fgrads[1], delta_posedirs=fgrads[2])
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # setup (not warm-up): every ring slot runs once, so that each of the N_RING workspaces / output sets exists and
-    # every kernel, peer mapping and function attribute has been used before anything is counted
-    for i in range(N_RING):
-        step(i)
+    # ---- setup (not warm-up) -------------------------------------------------------------------------------------
+    R.set_async(True)  # no host synchronisation inside the step; overflow is checked after the timed region
+    step(0)
+    torch.cuda.synchronize()
+    exchange_check = None
+    if dist is not None and not args.no_collective:
+        # SURVEY section 4 layer (4): the exchanged gradients must equal ONE rank summing the same N frames
+        got = {k: v.clone() for k, v in step(0).items()}
+        barrier()
+        if rank == 0:
+            want = None
+            tmp = torch.zeros(lay.n_splat, device=dev)
+            dense = [torch.zeros_like(t) for t in fgrads]
+            for r in range(world):
+                fr = parallel.AbiFrame(model, rs, *frame_inputs(r, 0))
+                fr.run(lay.views(tmp), record=None, dense=dense)
+                cur = dict(lay.views(tmp), delta_vertex=dense[0], delta_shapedirs=dense[1], delta_posedirs=dense[2])
+                want = {k: v.clone() for k, v in cur.items()} if want is None else {k: want[k] + cur[k] for k in want}
+            torch.cuda.synchronize()
+            errs = {k: float((got[k].reshape(-1) - want[k].reshape(-1)).abs().max() / want[k].abs().max().clamp_min(1e-30))
+                    for k in want}
+            exchange_check = {"max_rel_err": max(errs.values()), "per_part": {k: round(v, 9) for k, v in errs.items()},
+                              "what": f"summed gradients after the exchange vs rank 0 rendering all {world} ranks' frames and "
+                                      "adding them (float atomics reorder sums: tolerance 2e-4 of each part's max)"}
+            if not exchange_check["max_rel_err"] <= 2e-4:
+                raise SystemExit(f"exchange check failed: {exchange_check}")
+        barrier()
+    # every ring slot is recorded into its own CUDA graph (frame + exchange): the recording's eager warm-up runs each
+    # slot, so all N_RING workspaces / output sets exist and every kernel and peer mapping has been used before
+    # anything is counted; a step is then ONE graph launch and no host jitter leaks into the device timeline
+    use_graph = os.environ.get("FATESPLAT_BENCH_GRAPH", "1") == "1"
+    graphs = None
+    if use_graph:
+        from fateavatar_b200 import graph as fgraph
+
+        graphs = []
+        for k in range(N_RING):
+            graphs.append(fgraph.CapturedStep(lambda _inp, k=k: (step(k), {})[1], {}, params=(), warmup=2, device=dev))
+            barrier()
+    else:
+        for i in range(N_RING):
+            step(i)
+    R.set_async(True)
     barrier()
     R._drain_pending(R._pinned_slots(dev.index), dev.index, block=True)
+    run = (lambda i: graphs[i % N_RING].graph.replay()) if use_graph else step
+
     n_warm = max(args.warmup, 3)
     for i in range(n_warm):
-        step(i)
+        run(i)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -405,13 +398,16 @@ def main():
     barrier()
     e0.record()
     for i in range(args.steps):
-        step(i)
+        run(i)
     e1.record()
     barrier()
     sampler.stop_flag = True
     total_ms = e0.elapsed_time(e1)
     di = dev.index
-    R._drain_pending(R._pinned_slots(di), di, block=True)  # raises if any timed frame overflowed its workspace
+    if use_graph:
+        for g_ in graphs:
+            g_.check()  # raises if any replayed frame overflowed its workspace
+    R._drain_pending(R._pinned_slots(di), di, block=True)
     t_ms = torch.tensor([total_ms], device=dev)
     if dist is not None:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -419,17 +415,20 @@ def main():
     ms_per_step = total_ms / args.steps
     value = world * args.steps / (total_ms / 1000.0)
 
-    # ---- per-kernel device times (same loop, events around every stage launch) -----------------------------
+    # ---- per-kernel device times (the same step issued eagerly, events around every stage launch) ---------------
     lib = _lib.load()
     lib.fs_profile_enable(1)
     _lib.profile_read()
-    for i in range(args.steps):
+    for i in range(max(args.steps, 2 * N_RING)):
         step(i)
     torch.cuda.synchronize()
     prof = _lib.profile_read()
     lib.fs_profile_enable(0)
+    barrier()
     stage_us = {k: 1000.0 * v[0] / v[1] for k, v in prof.items() if v[1]}
-    taps = R.decode_workspace(ring[0]["workspace"], P, args.res, args.res, ring[0]["capacity"], -1)
+    st0 = abi[0].state
+    launches = [abi[0].launches + (0 if dist is None else (2 if getattr(getattr(sharded, "ex", None), "algo", "") == "two_shot" else 1))]
+    taps = R.decode_workspace(st0["workspace"], P, args.res, args.res, st0["capacity"], -1)
     Rn = int(taps["num_rendered"])
     Tn = ((args.res + 15) // 16) ** 2
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -448,9 +447,11 @@ def main():
            "preprocess": 52 * P + (40 + 12) * P,
            "preprocess_backward": (107 + 12) * P + (64 + 12) * P}
     traffic = {}
-    summ = os.path.join(ROOT, "profiles", "r01_summary.json")
-    if os.path.exists(summ):
-        traffic = json.load(open(summ)).get("dram_bytes_per_launch", {})
+    for summ in ("r02_summary.json", "r01_summary.json"):
+        sp = os.path.join(ROOT, "profiles", summ)
+        if os.path.exists(sp):
+            traffic = json.load(open(sp)).get("dram_bytes_per_launch", {})
+            break
     dom = "blend_backward"
     ach = alg[dom] / (stage_us[dom] * 1e-6) / 1e9 if dom in stage_us else None
     roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
@@ -464,13 +465,17 @@ def main():
     if args.quick:
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                              "ms_per_step": ms_per_step, "kernels": kernels, "quick": True}), file=REAL_STDOUT, flush=True)
+                              "ms_per_step": ms_per_step, "kernels": kernels, "exchange_check": exchange_check,
+                              "quick": True}), file=REAL_STDOUT, flush=True)
+        if dist is not None:
+            dist.destroy_process_group()
         return
 
-    # ---- e2e: public operator API, host buffers in, loss + image out --------------------------------------
+    # ---- e2e: public operator API, host buffers in, loss out -------------------------------------------------------
     # The splat parameters and the FLAME model are model state and stay on the device; what arrives from the host
     # every frame is the frame itself (train/dataset.py): expression + pose coefficients, camera matrices and the
-    # target image.
+    # target image.  The step is parallel.ShardedStep: avatar.forward_frame (= FateAvatar.forward) + L1 loss + backward
+    # under autograd, pack, fused exchange -- recorded into CUDA graphs, one launch per step.
     R.set_async(False)
     host = []
     cam_pose = np.eye(4, dtype=np.float32)  # what the dataset yields (train/dataset.py): c2w rotation, w2c translation
@@ -482,49 +487,36 @@ def main():
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
     out_loss = torch.empty(1).pin_memory()
     d2h = 4
-    leaves = [torch.nn.Parameter(p_.clone()) for p_ in params] + [torch.nn.Parameter(shs.clone())]
-    dleaves = {k: torch.nn.Parameter(v.clone()) for k, v in fdelta.items()}
-    # a FateAvatar look-alike: the attributes model/fateavatar.py keeps, driven through the caller-level mirror
-    # fateavatar_b200.avatar.forward_frame (= FateAvatar.forward: camera, FLAME x2, splat placement, render)
-    import types
-
-    from fateavatar_b200 import avatar
-
-    flame_mod = types.SimpleNamespace(n_shape=n_shape, n_exp=L - n_shape, parents=torch.tensor(f0["parents"]),
-                                      **{k: fmodel[k] for k in FLAME_KEYS})
-    model = types.SimpleNamespace(
-        flame=flame_mod, faces=faces, face_index=fidx, bary_coords=bary, face_scaling_canonical=canon,
-        _scaling=leaves[0], _rotation=leaves[1], _offset=leaves[2], _opacity=leaves[3], _features_dc=leaves[4],
-        delta_shapedirs=dleaves["delta_shapedirs"], delta_posedirs=dleaves["delta_posedirs"],
-        delta_vertex=dleaves["delta_vertex"], shell_len=f0["shell_len"], bg_color=bg, img_res=(args.res, args.res),
-        cfg_model=types.SimpleNamespace(delta_blendshape=True, delta_vertex=True, resize_scale=True))
     fov = [0.35]
+    all_leaves = [model._scaling, model._rotation, model._offset, model._opacity, model._features_dc,
+                  model.delta_shapedirs, model.delta_posedirs, model.delta_vertex]
+    e2e_sharded = sharded if sharded is not None else parallel.ShardedStep(model, device=dev) if world == 1 else None
 
-    def frame(d):
-        """One training frame through the public API under autograd; `d` holds this frame's inputs on the device."""
-        out = avatar.forward_frame(model, dict(cam_pose=d["cam_pose"], fovx=fov, fovy=fov, flame_pose=d["flame_pose"],
-                                               expression=d["expression"]))
-        loss = (out["rgb_image"][0] - d["target"]).abs().mean()
-        loss.backward()
-        return {"loss": loss.detach().reshape(1)}  # what a training step reads back (train/trainer.py: loss.item())
-
-    all_leaves = leaves + list(dleaves.values())
+    def frame_loss(m, d):
+        """One training frame through the public API; `d` holds this frame's inputs on the device."""
+        out = avatar.forward_frame(m, dict(cam_pose=d["cam_pose"], fovx=fov, fovy=fov, flame_pose=d["flame_pose"],
+                                           expression=d["expression"]))
+        return (out["rgb_image"][0] - d["target"]).abs().mean(), out
 
     def eager_step(i):  # every operator call issued from Python, default synchronous mode
         h = host[i % N_RING]
         d = {k: v.to(dev, non_blocking=True) for k, v in h.items()}
         for p_ in all_leaves:
             p_.grad = None
-        out = frame(d)
-        if dist is not None:
+        if e2e_sharded is not None:
+            loss, _ = e2e_sharded.run_autograd(i, frame_loss, d)
+            e2e_sharded.exchange(i)
+        else:
+            loss, _ = frame_loss(model, d)
+            loss.backward()
             for p_ in all_leaves:
                 dist.all_reduce(p_.grad)
-        out_loss.copy_(out["loss"], non_blocking=True)
+        out_loss.copy_(loss.detach().reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(out_loss[0])
 
     def time_e2e(fn, n):
-        for i in range(5):
+        for i in range(max(5, n_warm)):
             fn(i)
         barrier()
         e0.record()
@@ -539,31 +531,48 @@ def main():
 
     e2e_steps = max(10, min(args.steps, 200))
     eager_fps = time_e2e(eager_step, e2e_steps)
+    for p_ in all_leaves:
+        p_.grad = None
+    if e2e_sharded is not None:
+        # per step the host issues the H2D copies of this frame's pinned inputs, ONE graph launch (FLAME, pose, render,
+        # loss, backward, pack, fused exchange, D2H of the loss into pinned memory) and a stream synchronise before
+        # it reads the loss
+        e2e_sharded.capture(frame_loss, {k: v.to(dev) for k, v in host[0].items()})
+        barrier()
 
-    # the same frame recorded once into a CUDA graph (fateavatar_b200.graph.CapturedStep) and replayed: per step the
-    # host issues the H2D copies of this frame's pinned inputs, ONE graph launch (FLAME, pose, render, loss, backward,
-    # D2H of the loss into pinned memory) and a stream synchronise before it reads the loss
-    from fateavatar_b200 import graph as fgraph
+        def graph_step(i):
+            out = e2e_sharded(i, host[i % N_RING])
+            e2e_sharded.wait()
+            return float(out["loss"][0])
+        api = ("fateavatar_b200.parallel.ShardedStep (captured): avatar.forward_frame (the mirror of FateAvatar.forward: "
+               "camera, FLAME skinning, splat placement, GaussianRasterizer) + L1 loss + backward under autograd, gradient "
+               "pack and the fused peer-memory exchange, replayed as one CUDA graph per step; host inputs (expression, "
+               "pose, camera pose, target image) copied in and the loss copied out through pinned memory every step")
+    else:
+        from fateavatar_b200 import graph as fgraph
 
-    cap = fgraph.CapturedStep(frame, {k: v.to(dev) for k, v in host[0].items()}, params=all_leaves)
+        cap = fgraph.CapturedStep(lambda d: {"loss": (lambda l: (l.backward(), l.detach().reshape(1))[1])(frame_loss(model, d)[0])},
+                                  {k: v.to(dev) for k, v in host[0].items()}, params=all_leaves)
 
-    def graph_step(i):
-        out = cap(host[i % N_RING])
-        if dist is not None:
+        def graph_step(i):
+            out = cap(host[i % N_RING])
             for g_ in cap.grads:
                 dist.all_reduce(g_)
-        cap.wait()
-        return float(out["loss"][0])
+            cap.wait()
+            return float(out["loss"][0])
+        api = "graph.CapturedStep replaying avatar.forward_frame + L1 loss + backward; dense NCCL all-reduce per leaf"
 
     graph_fps = time_e2e(graph_step, e2e_steps)
     R.set_async(False)
     e2e = {"value": graph_fps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-           "api": "fateavatar_b200.graph.CapturedStep replaying one frame of fateavatar_b200.avatar.forward_frame (the mirror "
-                  "of FateAvatar.forward: camera, FLAME skinning, splat placement, GaussianRasterizer) under autograd with an "
-                  "L1 loss; host inputs (expression, pose, camera pose, target image) copied in and the loss copied out "
-                  "through pinned memory every step",
-           "eager_value": eager_fps,
-           "eager_api": "the same frame with every operator call issued from Python (default synchronous mode)"}
+           "api": api, "eager_value": eager_fps,
+           "eager_api": "the same step with every operator call issued from Python (default synchronous mode)"}
+    params = [p_.detach() for p_ in all_leaves[:4]]
+    shs = model._features_dc.detach()
+    fdelta = {k: getattr(model, k).detach() for k in DELTA_KEYS}
+    fmodel = {k: getattr(flame_mod, k) for k in FLAME_KEYS}
+    fidx, bary = model.face_index, model.bary_coords
+    betas, fpose, dpix = [a.betas for a in abi], [a.pose for a in abi], [a.dpix for a in abi]
 
     # ---- the reference's own CUDA rasterizer on the same GPU / frames (extra, rank 0) ----------------------
     gpu_ref = None
@@ -654,7 +663,9 @@ def main():
                 "warmup": n_warm, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(args), "exchange_mode": mode, "num_rendered": Rn, "clocks": sampler.summary(), "e2e": e2e,
-                "gpu_launches": launches[0] * args.steps, "gpu_launches_per_step": launches[0], "roofline": roofline,
+                "gpu_launches": launches[0] * args.steps, "gpu_launches_per_step": launches[0],
+                "step_issue": "one CUDA-graph launch per step" if use_graph else "eager C-ABI calls",
+                "exchange_check": exchange_check, "roofline": roofline,
                 "kernels": kernels, "cpu_baseline": cb, "gpu_reference": gpu_ref,
                 "speedup_vs_gpu_reference": (value / world / gpu_ref["value"]) if gpu_ref and "value" in gpu_ref else None}
         print(json.dumps(line), file=REAL_STDOUT, flush=True)

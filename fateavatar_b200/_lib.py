@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libfatesplat.so")
+# FATESPLAT_LIB: developer knob to load another build of the same library (kernel experiments); never a fallback
+LIB_PATH = os.environ.get("FATESPLAT_LIB") or os.path.join(_HERE, "lib", "libfatesplat.so")
 
 FS_OK = 0
 
@@ -39,6 +40,7 @@ EXPORTS = [
     "fs_knn_workspace_bytes", "fs_knn_mean_dist2", "fs_last_launch_count", "fs_last_error", "fs_version",
     "fs_profile_enable", "fs_profile_read", "fs_pose_forward", "fs_pose_backward", "fs_set_tile_hint",
     "fs_flame_workspace_bytes", "fs_flame_forward", "fs_flame_backward", "fs_flame_backward_coeffs", "fs_densify_stats", "fs_flame_expand_grads", "fs_p2p_allreduce", "fs_p2p_reduce_scatter_bcast",
+    "fs_p2p_exchange", "fs_p2p_wait", "fs_p2p_exchange_flag_floats", "fs_densify_stats_inc",
 ]
 
 STAGES = ["preprocess", "tile_scan", "scatter", "tile_sort", "big_tile_sort", "blend_forward", "blend_backward",
@@ -97,6 +99,14 @@ def load():
     lib.fs_p2p_reduce_scatter_bcast.argtypes = [i, i, vp, vp, sz, vp]
     lib.fs_p2p_allreduce.restype = i
     lib.fs_p2p_allreduce.argtypes = [i, vp, vp, sz, sz, vp, vp]
+    lib.fs_p2p_exchange_flag_floats.restype = sz
+    lib.fs_p2p_exchange_flag_floats.argtypes = []
+    lib.fs_p2p_exchange.restype = i
+    lib.fs_p2p_exchange.argtypes = [i, i, i, vp, vp, vp, sz, sz, sz, sz, sz, sz, vp, i, i, i, i, f, vp, vp, vp, vp]
+    lib.fs_p2p_wait.restype = i
+    lib.fs_p2p_wait.argtypes = [i, vp, sz, vp]
+    lib.fs_densify_stats_inc.restype = i
+    lib.fs_densify_stats_inc.argtypes = [i, vp, vp, vp, vp, vp]
     lib.fs_densify_stats.restype = i
     lib.fs_densify_stats.argtypes = [i, vp, vp, vp, vp, vp]
     lib.fs_set_tile_hint.restype = None

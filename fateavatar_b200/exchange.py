@@ -86,3 +86,85 @@ class SymmetricBucket:
                                       self.out_local.data_ptr(), stream)
             _lib.check(rc, "fs_p2p_allreduce")
         return self.out_local[:n]
+
+
+class StepExchange:
+    """The per-step exchange of frame-sharded training as ONE kernel (fs_p2p_exchange): cross-rank barrier, all-reduce
+    of the splat part of the bucket and expansion of the N FLAME factor records into the dense delta gradients.
+
+        ex = StepExchange(n_splat, rec_floats, device)       # collective (symmetric allocation + rendezvous)
+        b  = ex.fill(step)                                   # this step's bucket: [n_splat | world x rec_stride]
+        ... kernels write this rank's splat gradients into b[:n_splat] and its factor record into ex.record(step) ...
+        summed = ex.exchange(step, flame_dims, delta_out)    # one launch (+ fs_p2p_wait for the two-shot form)
+
+    Consecutive steps alternate between two input buckets, which makes the single in-kernel barrier sufficient (see
+    the module docstring).  No host synchronisation, no NCCL call, CUDA-graph capturable."""
+
+    ALGOS = {"one_shot": 0, "one_shot_mc": 1, "two_shot": 2}
+
+    def __init__(self, n_splat, rec_floats, device, group=None, algo=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        if not dist.is_initialized():
+            raise FateSplatError("StepExchange needs an initialised torch.distributed process group")
+        lib = _lib.load()
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.device = torch.device(device)
+        pad = lambda n, a: (int(n) + a - 1) // a * a
+        self.n_splat, self.rec_stride = pad(n_splat, 64), pad(rec_floats, 64)
+        self.bucket = self.n_splat + self.world * self.rec_stride
+        self.out_off = 2 * self.bucket
+        self.flags_off = self.out_off + self.n_splat
+        total = self.flags_off + pad(lib.fs_p2p_exchange_flag_floats(), 64)
+        self.mem = symm.empty(total, dtype=torch.float32, device=self.device)
+        self.mem.zero_()
+        self.hdl = symm.rendezvous(self.mem, self.group)
+        mc = int(self.hdl.multicast_ptr)
+        if algo is None:
+            algo = os.environ.get("FATESPLAT_P2P_ALGO", "auto")
+        if algo == "auto":  # measured on B200 / NVLink 5 (DESIGN.md 6): in-switch two-shot wins from 4 ranks
+            algo = "two_shot" if (self.world >= 4 and mc) else "one_shot"
+        if algo not in self.ALGOS:
+            raise FateSplatError(f"unknown exchange algorithm {algo!r} (one of {sorted(self.ALGOS)})")
+        if algo != "one_shot" and not mc:
+            raise FateSplatError(f"{algo} needs NVLink multicast (NVSwitch/NVLS), not available here")
+        self.algo = algo
+        self.multicast = mc or None
+        self.peer_ptrs_dev = int(self.hdl.buffer_ptrs_dev)
+        self.out_local = torch.empty(self.n_splat, dtype=torch.float32, device=self.device)
+        torch.cuda.synchronize(self.device)
+        self.hdl.barrier(channel=0)  # every rank's flags / buckets are zero before anybody signals
+
+    def fill(self, step):
+        k = step & 1
+        return self.mem[k * self.bucket:(k + 1) * self.bucket]
+
+    def record(self, step):
+        """This rank's slot among the N factor records of `step`'s bucket."""
+        o = (step & 1) * self.bucket + self.n_splat + self.rank * self.rec_stride
+        return self.mem[o:o + self.rec_stride]
+
+    def exchange(self, step, flame_dims=None, delta_out=(None, None, None), scale=1.0):
+        """flame_dims = (V, L, l0, NP); delta_out = (d_delta_vertex [V,3], d_delta_shapedirs [V,3,L], d_delta_posedirs
+        [NP,3V]) receive the summed dense gradients.  Returns the summed splat part (n_splat floats, rank-local)."""
+        lib = _lib.load()
+        V, L, l0, NP = flame_dims if flame_dims is not None else (0, 0, 0, 0)
+        p = lambda t: None if t is None else t.data_ptr()
+        a = self.ALGOS[self.algo]
+        with _lib.on_device(self.device):
+            st = _lib.stream_ptr(self.device)
+            rc = lib.fs_p2p_exchange(self.world, self.rank, a, self.peer_ptrs_dev, self.multicast, self.mem.data_ptr(),
+                                     (step & 1) * self.bucket, self.n_splat, self.n_splat, self.rec_stride, self.out_off,
+                                     self.flags_off, None if a == 2 else self.out_local.data_ptr(), V, L, l0, NP,
+                                     float(scale), p(delta_out[0]), p(delta_out[1]), p(delta_out[2]), st)
+            _lib.check(rc, "fs_p2p_exchange")
+            if a == 2:
+                _lib.check(lib.fs_p2p_wait(self.world, self.mem.data_ptr(), self.flags_off, st), "fs_p2p_wait")
+                return self.mem[self.out_off:self.out_off + self.n_splat]
+        return self.out_local
+
+    def summed(self):
+        """Where exchange() leaves the summed splat part (fixed address: valid to alias before the first call)."""
+        return self.mem[self.out_off:self.out_off + self.n_splat] if self.algo == "two_shot" else self.out_local

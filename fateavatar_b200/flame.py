@@ -107,6 +107,27 @@ def flame_backward_raw(betas, J_regressor, parents, lbs_weights, workspace, dL_d
     return (o[0], o[1], o[2]) + ((gs, gp) if factors else ())
 
 
+_factor_sink = [None]
+
+
+class factor_record:
+    """`with flame.factor_record(record):` -- while active, the backward of flame_lbs writes this frame's rank-1 factor
+    record [betas | pose_feature | dL/dv_shaped | dL/dv_posed] (factor_record_floats) into `record` INSTEAD of the
+    dense delta gradients (26 MB at FLAME size), and autograd delivers no gradient to delta_vertex / delta_shapedirs /
+    delta_posedirs.  Frame-sharded training exchanges the records and expands their sum (parallel.ShardedStep)."""
+
+    def __init__(self, record):
+        self.record, self.prev = record, None
+
+    def __enter__(self):
+        self.prev, _factor_sink[0] = _factor_sink[0], self.record
+        return self
+
+    def __exit__(self, *exc):
+        _factor_sink[0] = self.prev
+        return False
+
+
 class _FlameLBS(torch.autograd.Function):
     @staticmethod
     def forward(ctx, betas, pose, delta_vertex, delta_shapedirs, delta_posedirs, model, l0, want_orig):
@@ -134,6 +155,11 @@ class _FlameLBS(torch.autograd.Function):
         want = tuple(h and ctx.needs_input_grad[2 + i] for i, h in enumerate(ctx.have))
         want_b, want_p = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if g_verts is None or not (any(want) or want_b or want_p):
+            return (None,) * 8
+        if _factor_sink[0] is not None and any(want) and not (want_b or want_p):
+            flame_backward_raw(ctx.betas, m["J_regressor"], m["parents"], m["lbs_weights"], ctx.ws,
+                               g_verts.contiguous().float().reshape(V, 3), (V, L), l0=ctx.l0,
+                               want=(False, False, False), record=_factor_sink[0])
             return (None,) * 8
         gdv, gds, gdp = flame_backward_raw(ctx.betas, m["J_regressor"], m["parents"], m["lbs_weights"], ctx.ws,
                                            g_verts.contiguous().float().reshape(V, 3), (V, L), l0=ctx.l0, want=want)

@@ -242,6 +242,34 @@ int fs_p2p_reduce_scatter_bcast(int N, int rank, const float* d_multicast_in, fl
                                 void* stream);
 
 /*
+ * Fused exchange of one frame-sharded step (SURVEY 8e + 8f N4): cross-rank barrier + all-reduce of the splat-gradient
+ * part + expansion of the N factor records into the dense FLAME delta gradients, ONE kernel over peer memory.  It
+ * replaces, per step, [signal-pad barrier, fs_p2p_allreduce | fs_p2p_reduce_scatter_bcast (+ barrier),
+ * fs_flame_expand_grads] and -- like them -- stands where upstream would need an NCCL all-reduce (upstream trains on
+ * one GPU, train/base.py:54-60).  CUDA-graph capturable: the barrier epoch lives in device memory.
+ *
+ * Every rank owns one symmetric, peer-mapped allocation with the same layout (float offsets, multiples of 4):
+ *   [in_offset, +n_splat)                      this step's splat gradients (summed over ranks)
+ *   [in_offset + rec_offset + r*rec_stride, ..) rank r's factor record [betas L | pose_feature NP | dL/dv_shaped 3V |
+ *                                              dL/dv_posed 3V]; a rank fills only ITS slot, the others stay zero
+ *   [out_offset, +n_splat)                     algo 2: where the summed splat gradients land on every rank
+ *   [flags_offset, +fs_p2p_exchange_flag_floats())  zero-initialised once; owned by the library afterwards
+ * d_peer_ptrs: DEVICE array of the N ranks' unicast base addresses; d_multicast: multicast base or NULL;
+ * d_local_base: this rank's own base.  algo 0 = one-shot, unicast 128-bit peer loads summed in rank order (bitwise
+ * identical on all ranks); 1 = one-shot, multimem.ld_reduce through the switch; 2 = two-shot (each rank reduces its
+ * 1/N slice in the switch and multimem.st-broadcasts it; follow with fs_p2p_wait before reading out_offset).  For
+ * algo 0/1 the sum is written to the rank-local d_out.  The dense delta gradients (any may be NULL; all NULL = no
+ * FLAME part) are scale * sum over ranks of the records' outer products, as fs_flame_expand_grads.
+ * The caller alternates between two input buckets (in_offset) on consecutive steps; no other synchronisation.
+ */
+size_t fs_p2p_exchange_flag_floats(void);
+int fs_p2p_exchange(int N, int rank, int algo, const float* const* d_peer_ptrs, const float* d_multicast,
+                    float* d_local_base, size_t in_offset, size_t n_splat, size_t rec_offset, size_t rec_stride,
+                    size_t out_offset, size_t flags_offset, float* d_out, int V, int L, int l0, int NP, float scale,
+                    float* d_dL_ddelta_vertex, float* d_dL_ddelta_shapedirs, float* d_dL_ddelta_posedirs, void* stream);
+int fs_p2p_wait(int N, float* d_local_base, size_t flags_offset, void* stream);
+
+/*
  * Densification statistics (model/fateavatar.py:734-737, gaussian_model.py:418-420), in place:
  *   xyz_gradient_accum[i] += hypot(viewspace_grad[i,0], viewspace_grad[i,1]);  denom[i] += 1   where update_filter[i]
  * viewspace_grad [P,3] is the .grad of the dummy screen-space tensor (fs_backward's dL_dmeans2D), update_filter [P]
@@ -249,6 +277,10 @@ int fs_p2p_reduce_scatter_bcast(int N, int rank, const float* d_multicast_in, fl
  */
 int fs_densify_stats(int P, const float* d_viewspace_grad, const uint8_t* d_update_filter,
                      float* d_xyz_gradient_accum, float* d_denom, void* stream);
+/* Frame-sharded form of the same statistic: this frame's increments, written (not accumulated) -- hypot(grad) and 1
+ * where d_radii[i] > 0, else 0 -- so that they can travel in the gradient bucket and be summed over ranks. */
+int fs_densify_stats_inc(int P, const float* d_viewspace_grad, const int* d_radii, float* d_accum_inc,
+                         float* d_denom_inc, void* stream);
 
 /*
  * Optional per-stage device timing for bench.py's roofline figures.  While enabled, every stage launch is

@@ -143,7 +143,7 @@ def test_empty_and_all_culled(cuda_device):
 def test_capacity_overflow_is_retried_and_async_mode_detects_it(cuda_device, monkeypatch):
     sc = scenes.head_scene(P=6000, W=128, H=128, scale_mult=8.0, seed=31)
     o = oracle_forward(orc, sc)
-    monkeypatch.setattr(R, "_initial_capacity", lambda P, W, H, dev: 1024)  # far too small on purpose
+    monkeypatch.setattr(R, "_initial_capacity", lambda P, key: 1024)  # far too small on purpose
     color, radii, st, taps, _ = run_new(sc, cuda_device)
     assert st["capacity"] >= o["R"] > 1024
     check_forward_vs_oracle(color, radii, st, taps, o)

@@ -214,3 +214,46 @@ def test_frame_shard_sampler_and_synchronised_densify_world2():
     assert ep0[0] != ep0[1]                                           # reshuffled every epoch
     assert torch.equal(a0, torch.full((50, 1), 3.0)) and torch.equal(a0, a1) and torch.equal(d0, torch.full((50, 1), 4.0))
     assert torch.equal(picks0, picks1) and torch.equal(bary0, bary1)  # every rank densifies the same splats
+
+
+# ---- the frame-sharded step (parallel.ShardedStep / fs_p2p_exchange) ---------------------------------------------------
+def test_grad_layout_parts_are_disjoint_aligned_and_cover_the_bucket():
+    from fateavatar_b200 import flame, parallel
+
+    for P in (1, 7, 1000, 100001):
+        lay = parallel.GradLayout(P, V=50, L=40, NPF=36)
+        flat = torch.zeros(lay.n_splat)
+        v = lay.views(flat)
+        assert [n for n, _ in parallel.SPLAT_PARTS] == list(v)
+        for k, (name, width) in enumerate(parallel.SPLAT_PARTS):
+            assert v[name].shape == (P, width) and lay.offsets[name][0] % 4 == 0   # 16-byte aligned starts
+            v[name].fill_(k + 1)
+        for k, (name, width) in enumerate(parallel.SPLAT_PARTS):                 # nobody overwrote anybody
+            assert bool((v[name] == k + 1).all())
+        assert lay.rec_floats == flame.factor_record_floats(50, 40, 36) >= 40 + 36 + 6 * 50
+
+
+@pytest.mark.gpu
+def test_sharded_step_exchange_equals_single_rank_sum_on_two_gpus():
+    """SURVEY section 4 layer (4): after parallel.ShardedStep's fused peer-memory exchange every rank holds the gradients
+    ONE rank gets by rendering all ranks' frames and adding them (bench.py checks this in its setup and aborts
+    otherwise); the step is replayed from CUDA graphs afterwards, so the capture path is covered too."""
+    import json
+    import subprocess
+    import sys
+
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs with peer access")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(root, "bench.py"),
+                          "--gpus", "2", "--steps", "6", "--warmup", "3", "--quick", "--P", "20000", "--res", "256"],
+                         capture_output=True, text=True, timeout=900)
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert out.returncode == 0 and line, out.stderr[-3000:]
+    res = json.loads(line[-1])
+    assert res["n_gpus"] == 2 and res["exchange_check"]["max_rel_err"] <= 2e-4, res
