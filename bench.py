@@ -392,6 +392,8 @@ def main():
     for i in range(n_warm):
         run(i)
     barrier()
+    if sharded is not None and sharded.ex is not None:
+        sharded.ex.timing(reset=True)
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -404,6 +406,16 @@ def main():
     sampler.stop_flag = True
     total_ms = e0.elapsed_time(e1)
     di = dev.index
+    exchange_timing = None
+    if sharded is not None and sharded.ex is not None:
+        # device-side clock inside the exchange kernel over the timed steps: waiting for the slowest peer vs the work
+        exchange_timing = dict(sharded.ex.timing(reset=True), algo=sharded.ex.algo)
+        tt = torch.tensor([exchange_timing["wait_us"], exchange_timing["work_us"]], device=dev)
+        lo, hi = tt.clone(), tt.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        exchange_timing.update(wait_us_min_over_ranks=float(lo[0]), wait_us_max_over_ranks=float(hi[0]),
+                               work_us_max_over_ranks=float(hi[1]))
     if use_graph:
         for g_ in graphs:
             g_.check()  # raises if any replayed frame overflowed its workspace
@@ -466,7 +478,7 @@ def main():
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                               "ms_per_step": ms_per_step, "kernels": kernels, "exchange_check": exchange_check,
-                              "quick": True}), file=REAL_STDOUT, flush=True)
+                              "exchange_timing": exchange_timing, "quick": True}), file=REAL_STDOUT, flush=True)
         if dist is not None:
             dist.destroy_process_group()
         return
@@ -665,7 +677,7 @@ def main():
                 "config": workload_config(args), "exchange_mode": mode, "num_rendered": Rn, "clocks": sampler.summary(), "e2e": e2e,
                 "gpu_launches": launches[0] * args.steps, "gpu_launches_per_step": launches[0],
                 "step_issue": "one CUDA-graph launch per step" if use_graph else "eager C-ABI calls",
-                "exchange_check": exchange_check, "roofline": roofline,
+                "exchange_check": exchange_check, "exchange_timing": exchange_timing, "roofline": roofline,
                 "kernels": kernels, "cpu_baseline": cb, "gpu_reference": gpu_ref,
                 "speedup_vs_gpu_reference": (value / world / gpu_ref["value"]) if gpu_ref and "value" in gpu_ref else None}
         print(json.dumps(line), file=REAL_STDOUT, flush=True)

@@ -40,11 +40,11 @@ EXPORTS = [
     "fs_knn_workspace_bytes", "fs_knn_mean_dist2", "fs_last_launch_count", "fs_last_error", "fs_version",
     "fs_profile_enable", "fs_profile_read", "fs_pose_forward", "fs_pose_backward", "fs_set_tile_hint",
     "fs_flame_workspace_bytes", "fs_flame_forward", "fs_flame_backward", "fs_flame_backward_coeffs", "fs_densify_stats", "fs_flame_expand_grads", "fs_p2p_allreduce", "fs_p2p_reduce_scatter_bcast",
-    "fs_p2p_exchange", "fs_p2p_wait", "fs_p2p_exchange_flag_floats", "fs_densify_stats_inc",
+    "fs_p2p_exchange", "fs_p2p_wait", "fs_p2p_exchange_flag_floats", "fs_densify_stats_inc", "fs_p2p_exchange_timing",
 ]
 
 STAGES = ["preprocess", "tile_scan", "scatter", "tile_sort", "big_tile_sort", "blend_forward", "blend_backward",
-          "preprocess_backward", "knn", "pose_forward", "pose_backward", "flame_forward", "flame_backward"]
+          "preprocess_backward", "knn", "pose_forward", "pose_backward", "flame_forward", "flame_backward", "exchange"]
 
 _lib = None
 
@@ -102,7 +102,9 @@ def load():
     lib.fs_p2p_exchange_flag_floats.restype = sz
     lib.fs_p2p_exchange_flag_floats.argtypes = []
     lib.fs_p2p_exchange.restype = i
-    lib.fs_p2p_exchange.argtypes = [i, i, i, vp, vp, vp, sz, sz, sz, sz, sz, sz, vp, i, i, i, i, f, vp, vp, vp, vp]
+    lib.fs_p2p_exchange.argtypes = [i, i, i, vp, vp, vp, sz, sz, sz, sz, sz, sz, sz, vp, i, i, i, i, f, vp, vp, vp, vp]
+    lib.fs_p2p_exchange_timing.restype = i
+    lib.fs_p2p_exchange_timing.argtypes = [vp, sz, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int), i]
     lib.fs_p2p_wait.restype = i
     lib.fs_p2p_wait.argtypes = [i, vp, sz, vp]
     lib.fs_densify_stats_inc.restype = i

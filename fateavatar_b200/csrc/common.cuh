@@ -188,6 +188,7 @@ enum FsStage {
     FS_STAGE_POSE_BWD,
     FS_STAGE_FLAME_FWD,
     FS_STAGE_FLAME_BWD,
+    FS_STAGE_EXCHANGE,
     FS_STAGE_COUNT
 };
 struct FsStageTimer {  // RAII: records start in the ctor and stop in the dtor when profiling is on

@@ -8,6 +8,10 @@
 //   * unicast path: plain 128-bit loads from the N peer pointers, summed in rank order (bitwise identical on all ranks).
 // The sum lands in a rank-local buffer; the factor records of the FLAME delta gradients travel in the same bucket
 // (every rank fills only its own slot, so the sum is the all-gather) and are expanded by fs_flame_expand_grads.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace {
@@ -153,7 +157,7 @@ struct ExchangeArgs {
     const float* const* peers;         // device array: unicast base of every rank's symmetric allocation
     const float* mc;                   // multicast base (algo 1, 2) or nullptr
     float* local;                      // this rank's unicast base
-    size_t in_off, n_splat, rec_off, rec_stride, out_off, flags_off;
+    size_t in_off, n_splat, rec_off, rec_stride, out_off, flags_off, gather_off;
     float* out;                        // one-shot: rank-local destination of the splat part
     int V, L, l0, NP;
     float scale;
@@ -171,7 +175,15 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __device__ __forceinline__ float4 scale4(float4 v, float s) { return make_float4(v.x * s, v.y * s, v.z * s, v.w * s); }
 
 // flags (uint32) at local + flags_off:  [0, 8) arrive   [8, 16) done   [16] epoch   [17] CTAs finished
-constexpr int kFlagArrive = 0, kFlagDone = 8, kFlagEpoch = 16, kFlagCtas = 17;
+//                                        [20..21] t(barrier passed)  [24..25] sum ns waiting for peers  [26..27] sum ns
+//                                        of work after the barrier  [28] calls   (device-side timing, fs_p2p_exchange_timing)
+constexpr int kFlagArrive = 0, kFlagDone = 8, kFlagEpoch = 16, kFlagCtas = 17, kFlagReady = 18, kFlagTBar = 20, kFlagWait = 24,
+              kFlagWork = 26, kFlagCalls = 28, kFlagStage = 32, kFlagCta0 = 34;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 constexpr int kExThreads = 512;
 
 __device__ __forceinline__ float4 load_sum4(const ExchangeArgs& a, size_t i4 /* float4 index inside the bucket */) {
@@ -192,71 +204,119 @@ __device__ __forceinline__ float4 load_sum4(const ExchangeArgs& a, size_t i4 /* 
     return s;
 }
 
-__device__ void exchange_reduce_part(const ExchangeArgs& a, int cta, int nctas) {
+// One remote round trip per CTA: every load a CTA needs from its peers -- its share of the splat part, the heads of the
+// N factor records and the factor rows it will expand -- is issued before anything waits on one of them (NVLink loads
+// cost microseconds each; a dependent chain of them was the whole kernel time in the first version).
+constexpr int kStageUnroll = 8;
+
+__device__ __forceinline__ void reduce_store(const ExchangeArgs& a, size_t i, float4 x) {
+    x = scale4(x, a.scale);
+    if (a.algo == 2) multimem_st(const_cast<float*>(a.mc) + a.out_off + 4 * i, x);
+    else reinterpret_cast<float4*>(a.out)[i] = x;
+}
+
+// Gather once: the N factor records (122 KB each at FLAME size) cross the link ONCE per rank -- 4 CTAs per source rank
+// copy them into this rank's local gather area and raise a local counter; every CTA then stages what it needs from
+// local memory.  (Letting each of the ~300 CTAs pull the record heads from the peers itself put ~4 MB of redundant,
+// same-address traffic on every link and made the remote round trip 50 us at 8 ranks.)
+constexpr int kFetchPerRank = 4;
+
+__device__ __forceinline__ void exchange_body(const ExchangeArgs& a, float* smem) {
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const bool flame = a.d_dv || a.d_ds || a.d_dp;
+    const int n3 = 3 * a.V, LH = a.L + a.NP;
+    const int rpc = (n3 + gridDim.x - 1) / gridDim.x;             // factor rows expanded by one CTA
+    const int row0 = min(n3, (int)blockIdx.x * rpc), nrows = min(rpc, n3 - row0);
+    float* s_head = smem;                                          // [N][LH]
+    float* s_gs = smem + a.N * LH;                                 // [N][rpc]  dL/dv_shaped rows of this CTA
+    float* s_gp = s_gs + a.N * rpc;                                // [N][rpc]  dL/dv_posed rows of this CTA
+    uint32_t* flags = reinterpret_cast<uint32_t*>(a.local + a.flags_off);
+
+    // ---- splat part: this CTA's float4s of [lo, hi) ----
     const size_t n4 = a.n_splat / 4;
     size_t lo = 0, hi = n4;
-    if (a.algo == 2) {  // this rank's slice
+    if (a.algo == 2) {  // two-shot: only this rank's slice
         const size_t per = (n4 + a.N - 1) / a.N;
         lo = min(n4, per * (size_t)a.rank);
         hi = min(n4, lo + per);
     }
-    const size_t stride = (size_t)nctas * kExThreads;
-    size_t i = lo + (size_t)cta * kExThreads + threadIdx.x;
-    float4* out_local = reinterpret_cast<float4*>(a.out);
-    float* mc_out = const_cast<float*>(a.mc) + a.out_off;
-    for (; i + stride < hi; i += 2 * stride) {  // two requests in flight per thread
-        const float4 x = scale4(load_sum4(a, i), a.scale), y = scale4(load_sum4(a, i + stride), a.scale);
-        if (a.algo == 2) {
-            multimem_st(mc_out + 4 * i, x);
-            multimem_st(mc_out + 4 * (i + stride), y);
-        } else {
-            out_local[i] = x;
-            out_local[i + stride] = y;
-        }
-    }
-    for (; i < hi; i += stride) {
-        const float4 x = scale4(load_sum4(a, i), a.scale);
-        if (a.algo == 2) multimem_st(mc_out + 4 * i, x);
-        else out_local[i] = x;
-    }
-}
+    const size_t stride = (size_t)gridDim.x * kExThreads;
+    size_t i = lo + (size_t)blockIdx.x * kExThreads + t;
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+    const bool h0 = i < hi, h1 = i + stride < hi;
+    if (h0) r0 = load_sum4(a, i);            // in flight while the factor records are fetched
+    if (h1) r1 = load_sum4(a, i + stride);
 
-// factor element `e` of rank r's record (record layout: [betas L | pose_feature NP | dL/dv_shaped 3V | dL/dv_posed 3V])
-__device__ __forceinline__ float rec_ld(const ExchangeArgs& a, int r, size_t e) {
-    return __ldcv(a.peers[r] + a.in_off + a.rec_off + (size_t)r * a.rec_stride + e);
-}
-
-__device__ void exchange_expand_part(const ExchangeArgs& a, int cta, int nctas, float* s_head /* [N][L + NP] */) {
-    if (!a.d_dv && !a.d_ds && !a.d_dp) return;
-    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    const int n3 = 3 * a.V, LH = a.L + a.NP;
-    // heads of all N records -> shared memory (read straight from each owner's slot: only that slot is non-zero)
-    for (int e = t; e < a.N * LH; e += kExThreads) s_head[e] = rec_ld(a, e / LH, (size_t)(e % LH));
-    __syncthreads();
-    const size_t o_gs = (size_t)LH, o_gp = (size_t)LH + n3;
-    if (a.d_dp) {
-        for (int e = cta * kExThreads + t; e < n3; e += nctas * kExThreads) {
-            float g[FS_FLAME_MAX_RANKS];
+    const int fetchers = min((int)gridDim.x, kFetchPerRank * a.N);
+    if (flame && (int)blockIdx.x < fetchers) {
+        const int r = blockIdx.x / kFetchPerRank, q = blockIdx.x % kFetchPerRank;
+        const int rec4 = (LH + 2 * n3 + 3) / 4, per = (rec4 + kFetchPerRank - 1) / kFetchPerRank;
+        const int lo4 = min(rec4, q * per), hi4 = min(rec4, lo4 + per);
+        const float4* src = reinterpret_cast<const float4*>(a.peers[r] + a.in_off + a.rec_off + (size_t)r * a.rec_stride);
+        float4* dst = reinterpret_cast<float4*>(a.local + a.gather_off + (size_t)r * a.rec_stride);
+        for (int base = lo4; base < hi4; base += kStageUnroll * kExThreads) {
+            float4 v[kStageUnroll];
 #pragma unroll
-            for (int r = 0; r < FS_FLAME_MAX_RANKS; ++r) g[r] = r < a.N ? rec_ld(a, r, o_gp + e) * a.scale : 0.0f;
-            for (int i = 0; i < a.NP; ++i) {
-                float o = 0.f;
+            for (int u = 0; u < kStageUnroll; ++u) {
+                const int e = base + u * kExThreads + t;
+                if (e < hi4) v[u] = __ldcv(src + e);
+            }
 #pragma unroll
-                for (int r = 0; r < FS_FLAME_MAX_RANKS; ++r)
-                    if (r < a.N) o += s_head[r * LH + a.L + i] * g[r];
-                __stcs(a.d_dp + (size_t)i * n3 + e, o);
+            for (int u = 0; u < kStageUnroll; ++u) {
+                const int e = base + u * kExThreads + t;
+                if (e < hi4) __stcg(dst + e, v[u]);
             }
         }
+        __threadfence();
+        __syncthreads();
+        if (t == 0) atomicAdd(flags + kFlagReady, 1u);
     }
-    const int nw = nctas * (kExThreads / 32);
+    if (h0) reduce_store(a, i, r0);
+    if (h1) reduce_store(a, i + stride, r1);
+    for (i += 2 * stride; i < hi; i += stride) reduce_store(a, i, load_sum4(a, i));
+    if (!flame) return;
+    if (t == 0) {
+        while (*reinterpret_cast<volatile uint32_t*>(flags + kFlagReady) < (uint32_t)fetchers) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    {   // stage the heads of all records and this CTA's factor rows from the local gather area (L2)
+        const float* g = a.local + a.gather_off;
+        for (int e = t; e < a.N * LH; e += kExThreads) s_head[e] = __ldcg(g + (size_t)(e / LH) * a.rec_stride + (e % LH));
+        for (int e = t; e < a.N * nrows; e += kExThreads) {
+            const int r = e / nrows, k = e - r * nrows;
+            s_gs[r * rpc + k] = __ldcg(g + (size_t)r * a.rec_stride + LH + row0 + k) * a.scale;
+            s_gp[r * rpc + k] = __ldcg(g + (size_t)r * a.rec_stride + LH + n3 + row0 + k) * a.scale;
+        }
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && t == 0) {
+        uint32_t* fl = reinterpret_cast<uint32_t*>(a.local + a.flags_off);
+        *reinterpret_cast<unsigned long long*>(fl + kFlagStage) +=
+            globaltimer_ns() - *reinterpret_cast<volatile unsigned long long*>(fl + kFlagTBar);
+    }
+
+    // ---- expansion of this CTA's rows, from shared memory only ----
+    if (a.d_dp) {  // d_delta_posedirs[i][e] = sum_r pose_feature_r[i] * g_posed_r[e]
+        for (int q = t; q < a.NP * nrows; q += kExThreads) {
+            const int ii = q / nrows, k = q - ii * nrows;
+            float o = 0.f;
+#pragma unroll
+            for (int r = 0; r < FS_FLAME_MAX_RANKS; ++r)
+                if (r < a.N) o += s_head[r * LH + a.L + ii] * s_gp[r * rpc + k];
+            __stcs(a.d_dp + (size_t)ii * n3 + row0 + k, o);
+        }
+    }
     const bool vec = (a.L & 3) == 0 && (a.l0 & 3) == 0 && (LH & 3) == 0;
-    for (int row = cta * (kExThreads / 32) + wid; row < n3; row += nw) {
+    for (int k = wid; k < nrows; k += kExThreads / 32) {
         float gs[FS_FLAME_MAX_RANKS], sum = 0.f;
 #pragma unroll
         for (int r = 0; r < FS_FLAME_MAX_RANKS; ++r) {
-            gs[r] = r < a.N ? rec_ld(a, r, o_gs + row) * a.scale : 0.0f;
+            gs[r] = r < a.N ? s_gs[r * rpc + k] : 0.0f;
             sum += gs[r];
         }
+        const int row = row0 + k;
         if (lane == 0 && a.d_dv) a.d_dv[row] = sum;
         if (!a.d_ds) continue;
         float* out = a.d_ds + (size_t)row * a.L;
@@ -291,10 +351,14 @@ __device__ void exchange_expand_part(const ExchangeArgs& a, int cta, int nctas, 
 
 __global__ void __launch_bounds__(kExThreads)
 p2p_exchange_kernel(const ExchangeArgs a) {
-    extern __shared__ __align__(16) float s_head[];
+    extern __shared__ __align__(16) float s_dyn[];
     __shared__ uint32_t s_epoch;
     uint32_t* flags = reinterpret_cast<uint32_t*>(a.local + a.flags_off);
-    if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile uint32_t*>(flags + kFlagEpoch) + 1u;
+    unsigned long long t_entry = 0;
+    if (threadIdx.x == 0) {
+        s_epoch = *reinterpret_cast<volatile uint32_t*>(flags + kFlagEpoch) + 1u;
+        if (blockIdx.x == 0) t_entry = globaltimer_ns();
+    }
     __syncthreads();
     const uint32_t epoch = s_epoch;
     if (blockIdx.x == 0 && threadIdx.x < a.N) {
@@ -307,26 +371,30 @@ p2p_exchange_kernel(const ExchangeArgs a) {
         while ((int32_t)(ld_acquire_sys(flags + kFlagArrive + threadIdx.x) - epoch) < 0) {
         }
     __syncthreads();
-    const int half = gridDim.x / 2, odd = blockIdx.x & 1, idx = blockIdx.x >> 1;
-    // even CTAs: wire first; odd CTAs: local stores first (gridDim.x is even)
-    if (!odd) {
-        exchange_reduce_part(a, idx, half);
-        exchange_expand_part(a, blockIdx.x, gridDim.x, s_head);
-    } else {
-        exchange_expand_part(a, blockIdx.x, gridDim.x, s_head);
-        exchange_reduce_part(a, half - 1 - idx, half);  // (mirrored so that the two halves meet in the middle)
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned long long t = globaltimer_ns();
+        *reinterpret_cast<volatile unsigned long long*>(flags + kFlagTBar) = t;
+        *reinterpret_cast<unsigned long long*>(flags + kFlagWait) += t - t_entry;
     }
+    exchange_body(a, s_dyn);
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        *reinterpret_cast<unsigned long long*>(flags + kFlagCta0) +=
+            globaltimer_ns() - *reinterpret_cast<volatile unsigned long long*>(flags + kFlagTBar);
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence_system();  // this CTA's multicast stores are performed before it counts as finished
         const uint32_t prev = atomicAdd(flags + kFlagCtas, 1u);
         if (prev == gridDim.x - 1) {
             flags[kFlagCtas] = 0u;
+            flags[kFlagReady] = 0u;
             if (a.algo == 2)
                 for (int r = 0; r < a.N; ++r) {
                     uint32_t* pf = reinterpret_cast<uint32_t*>(const_cast<float*>(a.peers[r]) + a.flags_off);
                     st_release_sys(pf + kFlagDone + a.rank, epoch);
                 }
+            *reinterpret_cast<unsigned long long*>(flags + kFlagWork) +=
+                globaltimer_ns() - *reinterpret_cast<volatile unsigned long long*>(flags + kFlagTBar);
+            flags[kFlagCalls] += 1u;
             __threadfence();
             *reinterpret_cast<volatile uint32_t*>(flags + kFlagEpoch) = epoch;
         }
@@ -343,16 +411,43 @@ __global__ void p2p_wait_kernel(int N, uint32_t* flags) {
 
 }  // namespace
 
-extern "C" size_t fs_p2p_exchange_flag_floats(void) { return 32; }
+extern "C" size_t fs_p2p_exchange_flag_floats(void) { return 64; }
+
+// Device-side timing of the exchange kernel since the last reset (host call, synchronises the device): mean ns a rank
+// spent waiting in the barrier for its peers, mean ns from the barrier to the last CTA's exit, number of calls.
+extern "C" int fs_p2p_exchange_timing(float* d_local_base, size_t flags_offset, double* wait_ns, double* work_ns,
+                                      int* calls, int reset) {
+    uint32_t h[64];
+    if (cudaMemcpy(h, d_local_base + flags_offset, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        fs_set_error("fs_p2p_exchange_timing: copy failed");
+        return FS_ERR_CUDA;
+    }
+    unsigned long long w, k;
+    memcpy(&w, h + kFlagWait, 8);
+    memcpy(&k, h + kFlagWork, 8);
+    const int n = (int)h[kFlagCalls];
+    if (calls) *calls = n;
+    if (wait_ns) *wait_ns = n ? (double)w / n : 0.0;
+    if (work_ns) *work_ns = n ? (double)k / n : 0.0;
+    if (getenv("FATESPLAT_EXCHANGE_TRACE")) {
+        unsigned long long s1, s2;
+        memcpy(&s1, h + kFlagStage, 8);
+        memcpy(&s2, h + kFlagCta0, 8);
+        fprintf(stderr, "[fs_p2p_exchange] calls %d: wait %.1f us, CTA0 staged after %.1f us, CTA0 done after %.1f us, last CTA after %.1f us\n",
+                n, n ? w / 1e3 / n : 0.0, n ? s1 / 1e3 / n : 0.0, n ? s2 / 1e3 / n : 0.0, n ? k / 1e3 / n : 0.0);
+    }
+    if (reset) cudaMemset(reinterpret_cast<uint32_t*>(d_local_base + flags_offset) + kFlagWait, 0, 12 * sizeof(uint32_t));
+    return FS_OK;
+}
 
 extern "C" int fs_p2p_exchange(int N, int rank, int algo, const float* const* d_peer_ptrs, const float* d_multicast,
                                float* d_local_base, size_t in_offset, size_t n_splat, size_t rec_offset,
-                               size_t rec_stride, size_t out_offset, size_t flags_offset, float* d_out, int V, int L,
-                               int l0, int NP, float scale, float* d_dL_ddelta_vertex, float* d_dL_ddelta_shapedirs,
+                               size_t rec_stride, size_t out_offset, size_t flags_offset, size_t gather_offset,
+                               float* d_out, int V, int L, int l0, int NP, float scale, float* d_dL_ddelta_vertex, float* d_dL_ddelta_shapedirs,
                                float* d_dL_ddelta_posedirs, void* stream) {
     const bool flame = d_dL_ddelta_vertex || d_dL_ddelta_shapedirs || d_dL_ddelta_posedirs;
     if (N < 1 || N > FS_FLAME_MAX_RANKS || rank < 0 || rank >= N || algo < 0 || algo > 2 || !d_peer_ptrs || !d_local_base ||
-        ((in_offset | n_splat | rec_offset | rec_stride | out_offset | flags_offset) & 3) != 0 ||
+        ((in_offset | n_splat | rec_offset | rec_stride | out_offset | flags_offset | gather_offset) & 3) != 0 ||
         (algo != 0 && !d_multicast) || (algo != 2 && !d_out) ||
         (flame && (V <= 0 || L <= 0 || NP < 0 || l0 < 0 || l0 > L || rec_stride < (size_t)L + NP + 6 * (size_t)V))) {
         fs_set_error("fs_p2p_exchange: invalid argument (1 <= N <= %d, offsets multiples of 4 floats, multicast base for "
@@ -362,9 +457,11 @@ extern "C" int fs_p2p_exchange(int N, int rank, int algo, const float* const* d_
     ExchangeArgs a;
     a.N = N; a.rank = rank; a.algo = algo; a.peers = d_peer_ptrs; a.mc = d_multicast; a.local = d_local_base;
     a.in_off = in_offset; a.n_splat = n_splat; a.rec_off = rec_offset; a.rec_stride = rec_stride; a.out_off = out_offset;
-    a.flags_off = flags_offset; a.out = d_out; a.V = V; a.L = L; a.l0 = l0; a.NP = NP; a.scale = scale;
+    a.flags_off = flags_offset; a.gather_off = gather_offset; a.out = d_out; a.V = V; a.L = L; a.l0 = l0; a.NP = NP; a.scale = scale;
     a.d_dv = d_dL_ddelta_vertex; a.d_ds = d_dL_ddelta_shapedirs; a.d_dp = d_dL_ddelta_posedirs;
-    const size_t smem = flame ? (size_t)N * (L + NP) * sizeof(float) : 0;
+    const int grid = 2 * std::max(1, fs_tuning("FATESPLAT_EXCHANGE_CTAS_PER_SM", 1) * fs_num_sms());
+    const int rpc = flame ? (3 * V + grid - 1) / grid : 0;
+    const size_t smem = flame ? ((size_t)N * (L + NP) + 2 * (size_t)N * rpc) * sizeof(float) : 0;
     if (smem > 200 * 1024) {
         fs_set_error("fs_p2p_exchange: N * (L + NP) floats of record heads do not fit in shared memory");
         return FS_ERR_UNSUPPORTED;
@@ -372,8 +469,8 @@ extern "C" int fs_p2p_exchange(int N, int rank, int algo, const float* const* d_
     static std::atomic<unsigned long long> attr_set{0};
     if (fs_first_use_on_device(attr_set))
         cudaFuncSetAttribute(p2p_exchange_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    const int grid = 2 * std::max(1, fs_tuning("FATESPLAT_EXCHANGE_CTAS_PER_SM", 1) * fs_num_sms());
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FsStageTimer timer(FS_STAGE_EXCHANGE, st);
     p2p_exchange_kernel<<<grid, kExThreads, smem, st>>>(a);
     fs_count_launch(1);
     if (cudaGetLastError() != cudaSuccess) {

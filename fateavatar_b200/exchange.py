@@ -117,7 +117,8 @@ class StepExchange:
         self.bucket = self.n_splat + self.world * self.rec_stride
         self.out_off = 2 * self.bucket
         self.flags_off = self.out_off + self.n_splat
-        total = self.flags_off + pad(lib.fs_p2p_exchange_flag_floats(), 64)
+        self.gather_off = self.flags_off + pad(lib.fs_p2p_exchange_flag_floats(), 64)
+        total = self.gather_off + self.world * self.rec_stride
         self.mem = symm.empty(total, dtype=torch.float32, device=self.device)
         self.mem.zero_()
         self.hdl = symm.rendezvous(self.mem, self.group)
@@ -157,13 +158,26 @@ class StepExchange:
             st = _lib.stream_ptr(self.device)
             rc = lib.fs_p2p_exchange(self.world, self.rank, a, self.peer_ptrs_dev, self.multicast, self.mem.data_ptr(),
                                      (step & 1) * self.bucket, self.n_splat, self.n_splat, self.rec_stride, self.out_off,
-                                     self.flags_off, None if a == 2 else self.out_local.data_ptr(), V, L, l0, NP,
+                                     self.flags_off, self.gather_off, None if a == 2 else self.out_local.data_ptr(),
+                                     V, L, l0, NP,
                                      float(scale), p(delta_out[0]), p(delta_out[1]), p(delta_out[2]), st)
             _lib.check(rc, "fs_p2p_exchange")
             if a == 2:
                 _lib.check(lib.fs_p2p_wait(self.world, self.mem.data_ptr(), self.flags_off, st), "fs_p2p_wait")
                 return self.mem[self.out_off:self.out_off + self.n_splat]
         return self.out_local
+
+    def timing(self, reset=True):
+        """Device-side clock of the exchange kernel since the last reset: {"wait_us": mean time this rank spent in the
+        barrier waiting for its peers, "work_us": mean time from the barrier to the kernel's end, "calls"}."""
+        import ctypes as C
+
+        w, k, n = C.c_double(), C.c_double(), C.c_int()
+        with _lib.on_device(self.device):
+            rc = _lib.load().fs_p2p_exchange_timing(self.mem.data_ptr(), self.flags_off, C.byref(w), C.byref(k),
+                                                    C.byref(n), int(reset))
+        _lib.check(rc, "fs_p2p_exchange_timing")
+        return {"wait_us": w.value / 1e3, "work_us": k.value / 1e3, "calls": n.value}
 
     def summed(self):
         """Where exchange() leaves the summed splat part (fixed address: valid to alias before the first call)."""

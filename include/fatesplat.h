@@ -254,6 +254,7 @@ int fs_p2p_reduce_scatter_bcast(int N, int rank, const float* d_multicast_in, fl
  *                                              dL/dv_posed 3V]; a rank fills only ITS slot, the others stay zero
  *   [out_offset, +n_splat)                     algo 2: where the summed splat gradients land on every rank
  *   [flags_offset, +fs_p2p_exchange_flag_floats())  zero-initialised once; owned by the library afterwards
+ *   [gather_offset, +N*rec_stride)             local scratch: the N records are copied here once per step
  * d_peer_ptrs: DEVICE array of the N ranks' unicast base addresses; d_multicast: multicast base or NULL;
  * d_local_base: this rank's own base.  algo 0 = one-shot, unicast 128-bit peer loads summed in rank order (bitwise
  * identical on all ranks); 1 = one-shot, multimem.ld_reduce through the switch; 2 = two-shot (each rank reduces its
@@ -265,9 +266,14 @@ int fs_p2p_reduce_scatter_bcast(int N, int rank, const float* d_multicast_in, fl
 size_t fs_p2p_exchange_flag_floats(void);
 int fs_p2p_exchange(int N, int rank, int algo, const float* const* d_peer_ptrs, const float* d_multicast,
                     float* d_local_base, size_t in_offset, size_t n_splat, size_t rec_offset, size_t rec_stride,
-                    size_t out_offset, size_t flags_offset, float* d_out, int V, int L, int l0, int NP, float scale,
+                    size_t out_offset, size_t flags_offset, size_t gather_offset, float* d_out, int V, int L, int l0,
+                    int NP, float scale,
                     float* d_dL_ddelta_vertex, float* d_dL_ddelta_shapedirs, float* d_dL_ddelta_posedirs, void* stream);
 int fs_p2p_wait(int N, float* d_local_base, size_t flags_offset, void* stream);
+/* Device-side timing of fs_p2p_exchange since the last reset (synchronises the device): mean ns this rank waited in the
+ * barrier for its peers, mean ns from the barrier to the last CTA's exit, number of calls. */
+int fs_p2p_exchange_timing(float* d_local_base, size_t flags_offset, double* wait_ns, double* work_ns, int* calls,
+                           int reset);
 
 /*
  * Densification statistics (model/fateavatar.py:734-737, gaussian_model.py:418-420), in place:
@@ -286,9 +292,9 @@ int fs_densify_stats_inc(int P, const float* d_viewspace_grad, const int* d_radi
  * Optional per-stage device timing for bench.py's roofline figures.  While enabled, every stage launch is
  * bracketed by CUDA events on the launching stream; fs_profile_read waits for them and returns, per stage id
  * (0 preprocess, 1 tile_scan, 2 scatter, 3 tile_sort, 4 big_tile_sort, 5 blend_forward, 6 blend_backward,
- * 7 preprocess_backward, 8 knn, 9 pose_forward, 10 pose_backward, 11 flame_forward, 12 flame_backward), the summed milliseconds and the number of launches since the last read.
+ * 7 preprocess_backward, 8 knn, 9 pose_forward, 10 pose_backward, 11 flame_forward, 12 flame_backward, 13 exchange), the summed milliseconds and the number of launches since the last read.
  */
-#define FS_NUM_STAGES 13
+#define FS_NUM_STAGES 14
 void fs_profile_enable(int on);
 int fs_profile_read(float* total_ms, int* counts, int n);
 
