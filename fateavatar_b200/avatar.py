@@ -34,12 +34,30 @@ class FrameCamera:
     _proj_cache = {}
     _const_cache = {}
 
-    def __init__(self, R, T, FoVx, FoVy, img_res, znear=0.01, zfar=100.0):
+    def __init__(self, R, T, FoVx, FoVy, img_res, znear=0.01, zfar=100.0, exact=False):
+        """exact=True runs the reference's own sequence of library calls instead of the closed form -- Rt assembled on
+        the host, torch.linalg.inv twice on the CPU (tools/gs_utils/graphics_utils.py:51-62), upload, bmm, and the GPU
+        inverse for the camera centre (volume_rendering/camera_3dgs.py:53,71-72) -- so that view / projection matrices
+        carry the same fp32 bits as upstream and `radii`, which ceil() a function of them, cannot flip.  It costs the
+        host round trip the closed form exists to avoid and cannot be recorded into a CUDA graph."""
         R, T = R.reshape(3, 3), T.reshape(3)
         dev = R.device
         self.FoVx, self.FoVy = float(FoVx), float(FoVy)
         self.image_height, self.image_width = int(img_res[0]), int(img_res[1])
         self.znear, self.zfar = znear, zfar
+        if exact:
+            Rt = torch.zeros((4, 4))
+            Rt[:3, :3] = R.transpose(0, 1)
+            Rt[:3, 3] = T
+            Rt[3, 3] = 1.0
+            C2W = torch.linalg.inv(Rt)
+            C2W[:3, 3] = (C2W[:3, 3] + torch.tensor([.0, .0, .0])) * 1.0
+            view = torch.linalg.inv(C2W).float().transpose(0, 1).to(dev)
+            proj = self._projection(dev)
+            self.world_view_transform, self.projection_matrix = view, proj
+            self.full_proj_transform = view.unsqueeze(0).bmm(proj.unsqueeze(0)).squeeze(0)
+            self.camera_center = view.inverse()[3, :3]
+            return
         consts = FrameCamera._const_cache.get(str(dev))
         if consts is None:  # built once per device, outside any CUDA-graph capture (warm-up frames come first)
             consts = (torch.zeros(3, 1, device=dev), torch.ones(1, 1, device=dev))
@@ -48,20 +66,31 @@ class FrameCamera:
         # world_view_transform = Rt^T = [[R, 0], [T, 1]]; assembled from device tensors only (capture-safe)
         view = torch.cat([torch.cat([R32, consts[0]], dim=1), torch.cat([T32[None], consts[1]], dim=1)], dim=0)
         self.world_view_transform = view
-        key = (self.FoVx, self.FoVy, znear, zfar, str(dev))
-        proj = FrameCamera._proj_cache.get(key)
-        if proj is None:  # tools/gs_utils/graphics_utils.py:64-84, transposed
-            tx, ty = math.tan(self.FoVx / 2), math.tan(self.FoVy / 2)
-            P = torch.zeros(4, 4)
-            P[0, 0], P[1, 1] = 1.0 / tx, 1.0 / ty
-            P[3, 2] = 1.0
-            P[2, 2] = zfar / (zfar - znear)
-            P[2, 3] = -(zfar * znear) / (zfar - znear)
-            proj = P.t().contiguous().to(dev)
-            FrameCamera._proj_cache[key] = proj
+        proj = self._projection(dev)
         self.projection_matrix = proj
         self.full_proj_transform = view @ proj
         self.camera_center = -(R32 @ T32)
+
+    def _projection(self, dev):
+        """getProjectionMatrix (tools/gs_utils/graphics_utils.py:64-84) in the reference's own arithmetic, transposed;
+        cached per (fov, clip planes, device)."""
+        znear, zfar = self.znear, self.zfar
+        key = (self.FoVx, self.FoVy, znear, zfar, str(dev))
+        proj = FrameCamera._proj_cache.get(key)
+        if proj is None:
+            top, right = math.tan(self.FoVy / 2) * znear, math.tan(self.FoVx / 2) * znear
+            bottom, left = -top, -right
+            P = torch.zeros(4, 4)
+            P[0, 0] = 2.0 * znear / (right - left)
+            P[1, 1] = 2.0 * znear / (top - bottom)
+            P[0, 2] = (right + left) / (right - left)
+            P[1, 2] = (top + bottom) / (top - bottom)
+            P[3, 2] = 1.0
+            P[2, 2] = 1.0 * zfar / (zfar - znear)
+            P[2, 3] = -(zfar * znear) / (zfar - znear)
+            proj = P.transpose(0, 1).contiguous().to(dev)
+            FrameCamera._proj_cache[key] = proj
+        return proj
 
 
 def quaternion_to_axis_angle(q):
@@ -75,13 +104,17 @@ def quaternion_to_axis_angle(q):
     return q[..., 1:] / s
 
 
-def forward_frame(model, input):
-    """`model`: an object with FateAvatar's attributes (flame, faces, face_index, bary_coords, face_scaling_canonical,
+def forward_frame(model, input, exact_camera=None):
+    """`exact_camera` (default: `model.exact_camera` if set, else False) selects FrameCamera(exact=True).
+    `model`: an object with FateAvatar's attributes (flame, faces, face_index, bary_coords, face_scaling_canonical,
     _scaling, _rotation, _offset, _opacity, _features_dc, delta_shapedirs, delta_posedirs, delta_vertex, cfg_model,
     shell_len, bg_color, img_res, device); `input`: the dataset's dict (cam_pose, fovx, fovy, flame_pose, expression).
     Returns the dict of model/fateavatar.py:280-296."""
     cam_pose = input["cam_pose"]
-    camera = FrameCamera(cam_pose[:, :3, :3], cam_pose[:, :3, 3], input["fovx"][0], input["fovy"][0], model.img_res)
+    if exact_camera is None:
+        exact_camera = bool(getattr(model, "exact_camera", False))
+    camera = FrameCamera(cam_pose[:, :3, :3], cam_pose[:, :3, 3], input["fovx"][0], input["fovy"][0], model.img_res,
+                         exact=exact_camera)
     flame_pose, expression = input["flame_pose"], input["expression"]
     bs = flame_pose.shape[0]
     if bs != 1:
@@ -123,10 +156,10 @@ def forward_frame(model, input):
     }
 
 
-def attach(model):
+def attach(model, exact_camera=False):
     """Rebind the per-frame hot path of an existing reference FateAvatar instance: `forward`, the two FLAME methods and
     `_add_densification_stats`.  Nothing else of the model (densify / prune / checkpoints / inference) is touched."""
     _flame.attach(model.flame)
     _densify.attach(model)
-    model.forward = lambda input: forward_frame(model, input)
+    model.forward = lambda input: forward_frame(model, input, exact_camera=exact_camera)
     return model

@@ -3,7 +3,8 @@
 `render(viewpoint_camera, pc, bg_color, scaling_modifier, override_color, device)` has the reference's
 signature, argument meaning and return dict; it exists so tests/bench on a box without /root/reference can
 drive the operators exactly the way FateAvatar does.  With fateavatar_b200.install() the reference's own
-render_3dgs.py runs unchanged instead (tests/test_dropin_reference.py does that when the tree is present).
+render_3dgs.py runs unchanged instead (tests/test_dropin_reference_gpu.py does that on the B200 from the staged
+copy under oracle/_ref/pyref; tests/test_render_caller_cpu.py on the CPU oracle).
 
 `rasterizer_module` lets the tests substitute another implementation of the same operator API (the CPU
 oracle drop-in or the compiled reference) without touching this function.

@@ -220,13 +220,16 @@ def _smooth_skin_weights(rng, x, J):
     return np.exp(-d2 / 0.08 ** 2) + 1e-3
 
 
-def flame_inputs(seed=0, V=None, n_shape=300, n_exp=100, J=5, with_deltas=True):
+def flame_inputs(seed=0, V=None, n_shape=300, n_exp=100, J=5, with_deltas=True, v_template=None):
     """Synthetic FLAME-shaped model + one frame's coefficients (SURVEY Appendix C recipe): the licensed FLAME
     pickle cannot be shipped, so the buffers flame/FLAME.py:72-107 registers are drawn at FLAME's sizes and
     magnitudes (smooth blendshape fields of a few millimetres).  V=None uses the 5002-vertex ellipsoid template of
     `ellipsoid_mesh` (FLAME: 5023)."""
     rng = np.random.default_rng(seed)
-    if V is None:
+    if v_template is not None:  # e.g. the vertices of weights/head_template_mouth_close.obj (SURVEY 8d, config 2)
+        v_template = np.asarray(v_template, np.float64)
+        V = v_template.shape[0]
+    elif V is None:
         v_template, _ = ellipsoid_mesh()
         V = v_template.shape[0]
     else:
@@ -271,6 +274,39 @@ def small_avatar(seed=0, n_lat=9, n_lon=16, N=900):
         faces=faces, face_index=rng.choice(faces.shape[0], size=N, p=area / area.sum()).astype(np.int64),
         bary=rng.dirichlet(np.ones(3), N).astype(np.float32),
         scaling_raw=(np.log(6e-3) + 0.3 * rng.standard_normal((N, 3))).astype(np.float32),
+        rotation_raw=(np.array([1, 0, 0, 0], np.float32) + 0.5 * rng.standard_normal((N, 4))).astype(np.float32),
+        offset_raw=(0.5 * rng.standard_normal((N, 1))).astype(np.float32), opacity_raw=rng.standard_normal((N, 1)).astype(np.float32),
+        features_dc=((rng.uniform(0, 1, (N, 1, 3)) - 0.5) / SH_C0).astype(np.float32), shell_len=0.05)
+    return f
+
+
+def read_obj(path):
+    """(verts [V,3] float32, faces [F,3] int64, 0-based) of a triangulated Wavefront OBJ; only `v` and `f` lines are
+    read (pytorch3d.io.load_obj's verts / faces.verts_idx for the template mesh, model/fateavatar.py:123-127)."""
+    verts, faces = [], []
+    with open(path) as f:
+        for line in f:
+            if line.startswith("v "):
+                verts.append([float(x) for x in line.split()[1:4]])
+            elif line.startswith("f "):
+                idx = [int(tok.split("/")[0]) - 1 for tok in line.split()[1:]]
+                for k in range(1, len(idx) - 1):  # fan-triangulate (the template is already triangles)
+                    faces.append([idx[0], idx[k], idx[k + 1]])
+    return np.asarray(verts, np.float32), np.asarray(faces, np.int64)
+
+
+def template_avatar(verts, faces, N=100000, seed=0, scale=8e-4):
+    """SURVEY 8d's config-2 avatar on a given template mesh (the reference's head_template_mouth_close.obj: 5023
+    vertices, 10006 faces): FLAME-shaped model whose v_template is the re-centred mesh, N area-uniform splat sites,
+    raw splat parameters as FateAvatar stores them."""
+    rng = np.random.default_rng(seed)
+    f = flame_inputs(seed=seed, v_template=verts)
+    tri = f["v_template"][faces].astype(np.float64)
+    area = 0.5 * np.linalg.norm(np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]), axis=1)
+    f.update(
+        faces=faces, face_index=rng.choice(faces.shape[0], size=N, p=area / area.sum()).astype(np.int64),
+        bary=rng.dirichlet(np.ones(3), N).astype(np.float32),
+        scaling_raw=(np.log(scale) + 0.3 * rng.standard_normal((N, 3))).astype(np.float32),
         rotation_raw=(np.array([1, 0, 0, 0], np.float32) + 0.5 * rng.standard_normal((N, 4))).astype(np.float32),
         offset_raw=(0.5 * rng.standard_normal((N, 1))).astype(np.float32), opacity_raw=rng.standard_normal((N, 1)).astype(np.float32),
         features_dc=((rng.uniform(0, 1, (N, 1, 3)) - 0.5) / SH_C0).astype(np.float32), shell_len=0.05)

@@ -1,4 +1,6 @@
-"""Harness that executes the reference's UNCHANGED `FateAvatar.forward` (model/fateavatar.py:196-298) on the CPU.
+"""Harness that executes the reference's UNCHANGED `FateAvatar.forward` (model/fateavatar.py:196-298) -- on the CPU
+(rasterizer = the C oracle drop-in) or, on the GPU box, from the staged copies under oracle/_ref/pyref with the real
+drop-in (or the compiled reference) as `diff_gaussian_rasterization` (tests/test_dropin_reference_gpu.py).
 
 Used by tests/test_avatar_host.py and tests/golden/make_frame_golden.py.  The reference's own Camera, FLAME methods,
 mesh_compute / mesh_sampling functions, GaussianModel and render() run as they are; what is substituted:
@@ -43,10 +45,19 @@ class Patch:
         self._undo.clear()
 
 
-def load_reference(patch):
-    """Returns (FateAvatar class, FLAME class, mesh_compute module) loaded from the reference tree."""
+STAGED = __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))),
+                                    "oracle", "_ref", "pyref")
+
+
+def load_reference(patch, root=None, rasterizer="cpu", knn=None):
+    """Returns (FateAvatar class, FLAME class, mesh_compute module) loaded from the reference tree `root`.
+    rasterizer="cpu": the C-oracle drop-in, Tensor.cuda() patched to a no-op (CPU run).  Otherwise a module object that
+    provides the `diff_gaussian_rasterization` operator API (fateavatar_b200's drop-in or the compiled reference) and
+    nothing about devices is patched (GPU run); `knn` then provides simple_knn._C.distCUDA2."""
     from fateavatar_b200 import avatar
     from oracle import cpu_dropin, oracle as orc, pose_oracle as po
+
+    REF = root or globals()["REF"]
 
     def stub(name, **attrs):
         m = types.ModuleType(name)
@@ -72,7 +83,8 @@ def load_reference(patch):
          matrix_to_quaternion=po.matrix_to_quaternion, quaternion_multiply=po.quaternion_multiply)
     stub("plyfile", PlyData=object, PlyElement=object)
     stub("simple_knn")
-    stub("simple_knn._C", distCUDA2=lambda p: torch.from_numpy(orc.knn_mean_dist2(p.detach().cpu().numpy())))
+    stub("simple_knn._C", distCUDA2=knn if knn is not None else
+         (lambda p: torch.from_numpy(orc.knn_mean_dist2(p.detach().cpu().numpy()))))
     stub("tools")
     stub("tools.gs_utils")
     stub("tools.util", get_bg_color=lambda c: torch.ones(3) if c == "white" else torch.zeros(3))
@@ -81,21 +93,22 @@ def load_reference(patch):
     stub("flame")
     load("flame.lbs", f"{REF}/flame/lbs.py")
     FLAME = load("flame.FLAME", f"{REF}/flame/FLAME.py").FLAME
-    patch.setitem(sys.modules, "diff_gaussian_rasterization", cpu_dropin)
+    patch.setitem(sys.modules, "diff_gaussian_rasterization", cpu_dropin if rasterizer == "cpu" else rasterizer)
     stub("volume_rendering")
     for mod in ("camera_3dgs", "gaussian_model", "render_3dgs", "mesh_sampling", "mesh_compute"):
         load(f"volume_rendering.{mod}", f"{REF}/volume_rendering/{mod}.py")
     FateAvatar = load("ref_model_fateavatar", f"{REF}/model/fateavatar.py").FateAvatar
-    patch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    if rasterizer == "cpu":
+        patch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
     return FateAvatar, FLAME, sys.modules["volume_rendering.mesh_compute"]
 
 
 PARAMS = ("_scaling", "_rotation", "_offset", "_opacity", "_features_dc", "delta_vertex", "delta_posedirs", "delta_shapedirs")
 
 
-def build_reference_model(FateAvatar, FLAME, mesh_compute, a, img_res):
+def build_reference_model(FateAvatar, FLAME, mesh_compute, a, img_res, device="cpu"):
     """A reference FateAvatar instance whose state is the synthetic avatar `a` (scenes.small_avatar / equivalents)."""
-    t = lambda x: torch.from_numpy(np.asarray(x))
+    t = lambda x: torch.from_numpy(np.asarray(x)).to(device)
     flame_obj = FLAME.__new__(FLAME)
     torch.nn.Module.__init__(flame_obj)
     flame_obj.dtype, flame_obj.n_shape, flame_obj.n_exp = torch.float32, a["n_shape"], a["n_exp"]
@@ -108,18 +121,18 @@ def build_reference_model(FateAvatar, FLAME, mesh_compute, a, img_res):
     torch.nn.Module.__init__(ref)
     par = lambda x: torch.nn.Parameter(t(x).clone())
     N = a["face_index"].shape[0]
-    ref.flame, ref.device, ref.img_res, ref.shell_len = flame_obj, "cpu", tuple(img_res), a["shell_len"]
+    ref.flame, ref.device, ref.img_res, ref.shell_len = flame_obj, str(device), tuple(img_res), a["shell_len"]
     ref.cfg_model = types.SimpleNamespace(delta_blendshape=True, delta_vertex=True, resize_scale=True)
-    ref.bg_color = torch.ones(3)
+    ref.bg_color = torch.ones(3, device=device)
     ref.faces, ref.face_index, ref.bary_coords, ref.face_scaling_canonical = faces, t(a["face_index"]), t(a["bary"]), canon
     ref.delta_shapedirs, ref.delta_posedirs, ref.delta_vertex = par(a["delta_shapedirs"]), par(a["delta_posedirs"]), par(a["delta_vertex"])
-    ref._features_dc, ref._features_rest = par(a["features_dc"]), torch.zeros(N, 0, 3)
+    ref._features_dc, ref._features_rest = par(a["features_dc"]), torch.zeros(N, 0, 3, device=device)
     ref._scaling, ref._rotation, ref._offset, ref._opacity = par(a["scaling_raw"]), par(a["rotation_raw"]), par(a["offset_raw"]), par(a["opacity_raw"])
     return ref
 
 
-def frame_input(a, fovx=0.35, fovy=0.3, T=(0.02, -0.01, 1.25)):
-    t = lambda x: torch.from_numpy(np.asarray(x))
+def frame_input(a, fovx=0.35, fovy=0.3, T=(0.02, -0.01, 1.25), device="cpu"):
+    t = lambda x: torch.from_numpy(np.asarray(x)).to(device)
     cam_pose = np.eye(4, dtype=np.float32)
     cam_pose[:3, :3], cam_pose[:3, 3] = np.diag([1.0, -1.0, -1.0]), T
     return dict(cam_pose=t(cam_pose)[None], fovx=torch.tensor([fovx]), fovy=torch.tensor([fovy]),

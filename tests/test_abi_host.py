@@ -207,3 +207,19 @@ def test_uv_densify_with_synchronised_generator_keeps_replicas_identical():
     oa.zero_grad()
     sum((getattr(a, v) ** 2).sum() for v in parallel._ATTR_OF_GROUP.values()).backward()
     oa.step()                                                                            # the optimizer still works
+
+
+def test_staged_reference_callers_are_byte_identical_to_upstream():
+    """oracle/_ref/pyref (what tests/test_dropin_reference_gpu.py imports on the GPU box) must be the unchanged files."""
+    import importlib.util
+    import os
+
+    import pytest
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not (os.path.isdir("/root/reference") and os.path.exists(os.path.join(root, "oracle", "_ref", "pyref", "MANIFEST.sha256"))):
+        pytest.skip("reference tree or staged copy absent")
+    spec = importlib.util.spec_from_file_location("_stage", os.path.join(root, "oracle", "stage_ref_py.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    assert m.verify()

@@ -53,6 +53,10 @@ def test_frame_camera_matches_reference_graphics_utils():
     assert float((cam.projection_matrix - proj).abs().max()) <= 1e-6 * float(proj.abs().max())
     assert float((cam.full_proj_transform - full).abs().max()) <= 2e-5 * float(full.abs().max())
     assert float((cam.camera_center - center).abs().max()) <= 1e-5
+    # exact mode repeats the reference's own library calls: every matrix carries the same fp32 bits
+    ex = avatar.FrameCamera(Rt[None], Tt[None], 0.35, 0.3, (64, 64), exact=True)
+    assert torch.equal(ex.world_view_transform, view) and torch.equal(ex.projection_matrix, proj)
+    assert torch.equal(ex.full_proj_transform, full) and torch.equal(ex.camera_center, center)
 
 
 def test_quaternion_to_axis_angle_restatement_properties():

@@ -95,16 +95,12 @@ def test_backward_is_finite_linear_and_silent_where_nothing_was_drawn(case):
     assert all(not zero[k].any() for k in zero)
 
 
-# ---- the same scene family on the GPU (opt-in) ------------------------------------------------------------------------
-# Written in the last GPU-less hours of round 1 and therefore NOT yet run on a B200: it only executes when
-# FATESPLAT_PROPERTY_GPU=1 so that an unvalidated test cannot turn the suite red.  Enable it by default after one run.
-import os  # noqa: E402
-
+# ---- the same scene family on the GPU --------------------------------------------------------------------------------
+# (validated on a B200 in round 2 -- gpurun_out/c9_pytest.log -- and on by default since)
 import pytest  # noqa: E402
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("FATESPLAT_PROPERTY_GPU", "0") != "1", reason="opt-in until validated on a B200")
 @settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large,
                                                                  HealthCheck.function_scoped_fixture])
 @given(case=scene_strategy())

@@ -38,6 +38,14 @@ def test_forward_frame_kernels_match_golden_from_the_reference_forward(cuda_devi
         delta_vertex=par(a["delta_vertex"]), cfg_model=types.SimpleNamespace(delta_blendshape=True, delta_vertex=True, resize_scale=True),
         shell_len=a["shell_len"], bg_color=torch.ones(3, device=cuda_device), img_res=FRAME_RES)
     inp = {k: (v.to(cuda_device) if k in ("cam_pose", "flame_pose", "expression") else v) for k, v in H.frame_input(a).items()}
+    # exact-camera mode: the reference's own sequence of inverses, so the camera cannot flip a ceil()ed radius
+    out_x = avatar.forward_frame(model, inp, exact_camera=True)
+    n_flip = int((out_x["radii"][0].cpu().numpy() != gold["radii"]).sum())
+    dx = np.abs(out_x["rgb_image"][0].detach().cpu().numpy() - gold["rgb_image"])
+    print(f"[frame golden] exact camera: {n_flip} radii differ, image max|diff| {dx.max():.2e}")
+    # measured on the B200: 0 radii differ, image max|diff| 1.7e-6 (what remains is the fused FLAME / pose kernels'
+    # summation order, vertices <= 2e-6 m); asserted at the north_star bar: index outputs identical, image <= 1e-4
+    assert n_flip == 0 and dx.max() <= 1e-4
     out = avatar.forward_frame(model, inp)
     img = out["rgb_image"][0]
     diff = (img.detach().cpu().numpy() - gold["rgb_image"])
