@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--quick", action="store_true", help="device-resident arm only (used under ncu)")
     ap.add_argument("--no-collective", action="store_true", help="developer probe: skip the gradient exchange at N > 1")
+    ap.add_argument("--no-config3", action="store_true", help="skip the optimise-loop (config 3) extra")
+    ap.add_argument("--config3-steps", type=int, default=3200)
     return ap.parse_args()
 
 
@@ -208,6 +210,64 @@ def cpu_arm(args, frames, seconds, max_frames):
     return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{n} frames of the same workload (torch FLAME lbs + pose stage, C oracle rasterizer, forward+backward, "
                       f"{threads} threads) in {dt:.1f} s"}, dt / n
+
+
+def bench_config3(args, model, host, dev, avatar, torch, types):
+    """BASELINE.json configs[2]: the full optimise loop of config/fateavatar.yaml on the GPU path -- per step
+    avatar.forward_frame + loss (L1 + 0.1 scale regulariser + 1e5 Laplacian term of train/loss.py:123-204; the VGG term
+    needs ImageNet weights that cannot be fetched offline and is off) + backward + densification statistics + both Adam
+    steps, replayed as one CUDA graph (optimizer.OptimiseLoop); _uv_densify every 3000 steps, prune every 2000, with the
+    graph re-recorded when P changes.  Host inputs in (pinned H2D), loss out (D2H) every step, like the e2e arm."""
+    import copy
+
+    from fateavatar_b200 import optimizer as fopt
+
+    m3 = copy.copy(model)
+    for a in ("_scaling", "_rotation", "_offset", "_opacity", "_features_dc", "delta_shapedirs", "delta_posedirs", "delta_vertex"):
+        setattr(m3, a, torch.nn.Parameter(getattr(model, a).detach().clone()))
+    P0 = m3._scaling.shape[0]
+    m3.xyz_gradient_accum, m3.denom = torch.zeros(P0, 1, device=dev), torch.zeros(P0, 1, device=dev)
+    m3.max_radii2D, m3.sample_flag, m3.num_points = torch.zeros(P0, device=dev), torch.zeros(P0, device=dev), P0
+    f = m3.faces
+    e = torch.cat([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]], 0)
+    e = torch.unique(torch.cat([e, e.flip(1)], 0), dim=0)  # directed edges i -> j, each once
+    V = m3.flame.v_template.shape[0]
+    deg = torch.zeros(V, device=dev).index_add_(0, e[:, 0], torch.ones(e.shape[0], device=dev)).clamp_min(1.0)[:, None]
+    fov = [0.35]
+
+    def frame_loss(m, d):
+        out = avatar.forward_frame(m, dict(cam_pose=d["cam_pose"], fovx=fov, fovy=fov, flame_pose=d["flame_pose"],
+                                           expression=d["expression"]))
+        loss = (out["rgb_image"][0] - d["target"]).abs().mean()
+        sc = out["scale"]
+        loss = loss + 0.1 * torch.relu(sc.max(dim=-1)[0] / sc.min(dim=-1)[0] - 9.0).mean()
+        dv = (out["verts"] - out["verts_orig"].detach())[0]   # L verts - (L verts_orig).detach(), uniform Laplacian
+        lap = torch.zeros_like(dv).index_add_(0, e[:, 0], dv[e[:, 1]]) / deg - dv
+        return loss + 100000.0 * (lap ** 2).sum(-1).mean(), out
+
+    events = []
+    loop = fopt.OptimiseLoop(m3, frame_loss, {k: v.to(dev) for k, v in host[0].items()},
+                             generator=torch.Generator(device=dev).manual_seed(0), log=events.append)
+    n = max(10, args.config3_steps)
+    losses = []
+    loop.recording_s = 0.0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(n):
+        r = loop.step(host[i % len(host)])
+        loop.wait()
+        if i % 100 == 0 or i == n - 1:
+            losses.append(float(r["loss"][0]))
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"steps": n, "steps_per_s": n / dt, "ms_per_step": 1000.0 * dt / n,
+            "steady_steps_per_s": n / max(dt - loop.recording_s, 1e-9), "recording_s": loop.recording_s,
+            "P_start": P0, "P_end": loop.store.P,
+            "graph_recordings": loop.recaptures, "maintenance_events": len(events), "loss_first": losses[0],
+            "loss_last": losses[-1],
+            "what": "optimizer.OptimiseLoop: config/fateavatar.yaml's loop (densify 3000 / prune 2000 / max 200k) with "
+                    "L1 + scale + Laplacian loss, fused Adam, in-place densify / prune; wall clock including the graph "
+                    "re-recordings, pinned H2D of every frame's inputs and the loss read-back"}
 
 
 def main():
@@ -586,6 +646,14 @@ def main():
     fidx, bary = model.face_index, model.bary_coords
     betas, fpose, dpix = [a.betas for a in abi], [a.pose for a in abi], [a.dpix for a in abi]
 
+    # ---- config 3: the optimise loop (BASELINE.json configs[2]) ---------------------------------------------------
+    config3 = None
+    if rank == 0 and world == 1 and not args.no_config3:
+        try:
+            config3 = bench_config3(args, model, host, dev, avatar, torch, types)
+        except Exception as ex:  # never let an extra key break the contract line
+            config3 = {"error": repr(ex)[:300]}
+
     # ---- the reference's own CUDA rasterizer on the same GPU / frames (extra, rank 0) ----------------------
     gpu_ref = None
     if rank == 0:
@@ -678,7 +746,7 @@ def main():
                 "gpu_launches": launches[0] * args.steps, "gpu_launches_per_step": launches[0],
                 "step_issue": "one CUDA-graph launch per step" if use_graph else "eager C-ABI calls",
                 "exchange_check": exchange_check, "exchange_timing": exchange_timing, "roofline": roofline,
-                "kernels": kernels, "cpu_baseline": cb, "gpu_reference": gpu_ref,
+                "kernels": kernels, "cpu_baseline": cb, "gpu_reference": gpu_ref, "config3": config3,
                 "speedup_vs_gpu_reference": (value / world / gpu_ref["value"]) if gpu_ref and "value" in gpu_ref else None}
         print(json.dumps(line), file=REAL_STDOUT, flush=True)
     if dist is not None:

@@ -24,7 +24,7 @@ from ._lib import FateSplatError, FsFrameInfo
 
 
 class CapturedStep:
-    def __init__(self, frame_fn, example_inputs, params=(), warmup=3, device=None):
+    def __init__(self, frame_fn, example_inputs, params=(), warmup=3, device=None, on_capture=None):
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         dev = self.device
         self.params = list(params)
@@ -52,6 +52,8 @@ class CapturedStep:
         _R.set_async(True)
         n0 = len(_R.capture_headers)
         self.graph = torch.cuda.CUDAGraph()
+        if on_capture is not None:
+            on_capture()  # e.g. enable launches that must not run during the eager warm-up (an optimiser step)
         try:
             with torch.cuda.graph(self.graph):
                 out = frame_fn(self.static_in)

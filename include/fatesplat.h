@@ -289,6 +289,54 @@ int fs_densify_stats_inc(int P, const float* d_viewspace_grad, const int* d_radi
                          float* d_denom_inc, void* stream);
 
 /*
+ * Optimiser step and splat-set maintenance of the optimise loop, on the device.
+ *
+ * fs_adam_step replaces the two torch.optim.Adam instances over 8 parameter groups of train/optim.py:15-35 by ONE
+ * launch over up to FS_ADAM_MAX_TENSORS tensors (torch.optim.Adam arithmetic, betas / eps shared, one learning rate and
+ * one step counter per tensor).  d_steps: FS_ADAM_MAX_TENSORS + 1 device ints, zero-initialised by the caller; entry k
+ * counts the steps tensor k has taken (advanced by the kernel, so a recorded launch stays valid across CUDA-graph
+ * replays), the last entry is library scratch.
+ *
+ * fs_splat_soa names every array that has one row per splat in model/fateavatar.py (five parameters, their Adam
+ * moments -- NULL before the first step --, splat sites, densification statistics, flags), each allocated for a
+ * CAPACITY >= P rows, so that
+ *   fs_splat_append  (= _uv_densify, :610-672): rows [P, P+n) become children of d_parents[j] (parameters copied,
+ *                    scaling' = log(exp(scaling) * 0.75), moments 0, same face, barycentrics d_new_bary[j], flag 1) and
+ *                    the statistics of all P+n rows restart at 0;
+ *   fs_splat_prune   (= _prune_low_opacity_points, :674-713): rows with sigmoid(opacity) < min_opacity are dropped,
+ *                    the survivors of `in` are written in order to `out` (another SoA of the same capacity), their
+ *                    number to *d_new_P (device);
+ *   fs_opacity_reset (= _reset_opacity, :715-732): opacity = inverse_sigmoid(min(sigmoid(opacity), cap)), moments 0
+ * change P without reallocating or concatenating anything.
+ */
+#define FS_ADAM_MAX_TENSORS 8
+typedef struct fs_adam_tensor {
+    float* param;
+    const float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    size_t n;
+    float lr;
+} fs_adam_tensor;
+int fs_adam_step(int n_tensors, const fs_adam_tensor* h_tensors, int* d_steps, double beta1, double beta2, double eps,
+                 void* stream);
+typedef struct fs_splat_soa {
+    float *opacity, *offset, *color, *rotation, *scaling;  /* [cap,1] [cap,1] [cap,3] [cap,4] [cap,3] */
+    float* exp_avg[5];                                       /* same order and shapes; entries may be NULL */
+    float* exp_avg_sq[5];
+    long long* face_index;                                   /* [cap] */
+    float* bary;                                             /* [cap,3] */
+    float *accum, *denom;                                    /* xyz_gradient_accum, denom [cap,1] */
+    float *max_radii2D, *sample_flag;                        /* [cap], may be NULL */
+} fs_splat_soa;
+int fs_splat_append(const fs_splat_soa* soa, int P, int n, const long long* d_parents, const float* d_new_bary,
+                    void* stream);
+size_t fs_splat_prune_workspace_bytes(int P);
+int fs_splat_prune(const fs_splat_soa* in, const fs_splat_soa* out, int P, float min_opacity, int* d_new_P,
+                   void* d_workspace, size_t workspace_bytes, void* stream);
+int fs_opacity_reset(float* d_opacity, float* d_exp_avg, float* d_exp_avg_sq, int P, float cap, void* stream);
+
+/*
  * Optional per-stage device timing for bench.py's roofline figures.  While enabled, every stage launch is
  * bracketed by CUDA events on the launching stream; fs_profile_read waits for them and returns, per stage id
  * (0 preprocess, 1 tile_scan, 2 scatter, 3 tile_sort, 4 big_tile_sort, 5 blend_forward, 6 blend_backward,
