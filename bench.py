@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--quick", action="store_true", help="device-resident arm only (used under ncu)")
     ap.add_argument("--no-collective", action="store_true", help="developer probe: skip the gradient exchange at N > 1")
     ap.add_argument("--no-config3", action="store_true", help="skip the optimise-loop (config 3) extra")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config 1 / config 5 / simple-knn extras")
     ap.add_argument("--config3-steps", type=int, default=3200)
     return ap.parse_args()
 
@@ -210,6 +211,168 @@ def cpu_arm(args, frames, seconds, max_frames):
     return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{n} frames of the same workload (torch FLAME lbs + pose stage, C oracle rasterizer, forward+backward, "
                       f"{threads} threads) in {dt:.1f} s"}, dt / n
+
+
+def bench_extras(args, dev, torch):
+    """Extra keys (rank 0, one GPU): BASELINE.json configs[0] and configs[4] and the simple-knn query, each against the
+    compiled reference (oracle/_ref, when present) on the same inputs.
+
+    config1   10k random Gaussians, 256x256, forward only: frames/s of fs_forward (no host sync), of the reference's
+              rasterize_gaussians, and of the CPU port (C oracle, all host threads).
+    config5   1024x1024, 500k Gaussians, SH degree 3: forward over all 72 orbit views (R, visible splats and heaviest tile
+              per view), forward+backward on 8 of them.
+    knn       distCUDA2 at 65 536 / 100 000 / 500 000 points vs the reference's simple-knn."""
+    import numpy as np
+
+    from fateavatar_b200 import knn as fknn, rasterizer as R, scenes
+    from oracle import ref_loader
+
+    ref = ref_loader.ref_dgr() if ref_loader.available() else None
+    E = torch.Tensor([])
+
+    def ev_ms(fn, warm=3, iters=10):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    def wall_ms(fn, warm=3, iters=10):  # the reference launches on the legacy stream and blocks on num_rendered
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            fn()
+        torch.cuda.synchronize()
+        return 1000.0 * (time.perf_counter() - t0) / iters
+
+    def settings(t, cam, deg):
+        return R.GaussianRasterizationSettings(cam["H"], cam["W"], cam["tanfovx"], cam["tanfovy"], t["bg"], 1.0,
+                                               cam["viewmatrix"], cam["projmatrix"], deg, cam["campos"], False, False)
+
+    def ref_args(t, cam, deg):
+        return (t["bg"], t["means3D"], E, t["opacities"], t["scales"], t["rotations"], 1.0, E, cam["viewmatrix"],
+                cam["projmatrix"], cam["tanfovx"], cam["tanfovy"], cam["H"], cam["W"], t["shs"], deg, cam["campos"], False, False)
+
+    def ref_fwd_bwd(a, dpix):
+        Rr, c, rad, g, b, im = ref.rasterize_gaussians(*a)
+        ref.rasterize_gaussians_backward(a[0], a[1], rad, a[2], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], dpix,
+                                         a[14], a[15], a[16], g, Rr, b, im, False)
+
+    out = {}
+    R.set_async(True)
+    try:
+        # ---- config 1 ----
+        sc = scenes.config1_scene()
+        t = scenes.to_torch(sc, dev)
+        rs = settings(t, t["camera"], 0)
+        new_ms = ev_ms(lambda: R.forward_raw(rs, t["means3D"], t["shs"], None, t["opacities"], t["scales"], t["rotations"], None),
+                       warm=5, iters=50)
+        c1 = {"new_fps": 1000.0 / new_ms, "new_ms": new_ms}
+        try:  # the same forward recorded once and replayed (what a render loop does): no Python between the launches
+            from fateavatar_b200 import graph as fgraph
+
+            cap = fgraph.CapturedStep(lambda _i: (R.forward_raw(rs, t["means3D"], t["shs"], None, t["opacities"], t["scales"],
+                                                                t["rotations"], None), {})[1], {}, params=(), warmup=2, device=dev)
+            R.set_async(True)
+            g_ms = ev_ms(cap.graph.replay, warm=5, iters=200)
+            cap.check()
+            c1.update(new_graph_ms=g_ms, new_graph_fps=1000.0 / g_ms)
+        except Exception as ex:
+            c1["graph_error"] = repr(ex)[:200]
+        if ref is not None:
+            a = ref_args(t, t["camera"], 0)
+            c1["gpu_reference_ms"] = wall_ms(lambda: ref.rasterize_gaussians(*a), warm=5, iters=50)
+            c1["gpu_reference_fps"] = 1000.0 / c1["gpu_reference_ms"]
+            c1["speedup_vs_gpu_reference"] = c1["gpu_reference_ms"] / new_ms
+        try:
+            from oracle import oracle as orc
+
+            threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+            orc.set_num_threads(threads)
+            cam = sc["camera"]
+            f = lambda: orc.forward(sc["means3D"], sc["opacities"], sc["bg"], cam["viewmatrix"], cam["projmatrix"], cam["campos"],
+                                    cam["tanfovx"], cam["tanfovy"], cam["H"], cam["W"], shs=sc["shs"], sh_degree=0,
+                                    scales=sc["scales"], rotations=sc["rotations"])
+            f()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                f()
+            c1["cpu_port_fps"] = 5.0 / (time.perf_counter() - t0)
+            c1["cpu_port_threads"] = threads
+        except Exception as ex:
+            c1["cpu_port_error"] = repr(ex)[:200]
+        out["config1"] = c1
+
+        # ---- config 5 ----
+        sc = scenes.stress_scene(view=0)
+        t = scenes.to_torch(sc, dev)
+        P = t["means3D"].shape[0]
+        dpix = torch.randn(3, 1024, 1024, device=dev)
+        views, new_f, ref_f = [], [], []
+        for k in range(72):
+            cam = {kk: (torch.from_numpy(vv).to(dev) if isinstance(vv, np.ndarray) else vv)
+                   for kk, vv in scenes.orbit_camera(1024, 1024, 0.35, k, 72, radius=2.5).items()}
+            rs = settings(t, cam, 3)
+            fn = lambda: R.forward_raw(rs, t["means3D"], t["shs"], None, t["opacities"], t["scales"], t["rotations"], None)
+            ms = ev_ms(fn, warm=2, iters=3)
+            color, radii, st = fn()
+            torch.cuda.synchronize()
+            info = R.decode_workspace(st["workspace"], P, 1024, 1024, st["capacity"], -1)["info"].cpu().numpy()
+            v = {"view": k, "R": int(info[0]), "visible": int((radii > 0).sum()), "max_tile": int(info[3]), "new_fwd_ms": round(ms, 4)}
+            new_f.append(ms)
+            if ref is not None:
+                a = ref_args(t, cam, 3)
+                v["gpu_reference_fwd_ms"] = round(wall_ms(lambda: ref.rasterize_gaussians(*a), warm=1, iters=2), 4)
+                ref_f.append(v["gpu_reference_fwd_ms"])
+            if k % 9 == 0:
+                def fb():
+                    c_, r_, s_ = R.forward_raw(rs, t["means3D"], t["shs"], None, t["opacities"], t["scales"], t["rotations"], None)
+                    R.backward_raw(s_, dpix)
+                v["new_fwdbwd_ms"] = round(ev_ms(fb, warm=2, iters=3), 4)
+                if ref is not None:
+                    v["gpu_reference_fwdbwd_ms"] = round(wall_ms(lambda: ref_fwd_bwd(a, dpix), warm=1, iters=2), 4)
+            views.append(v)
+        c5 = {"views": 72, "new_fwd_ms_mean": float(np.mean(new_f)), "new_fwd_ms_max": float(np.max(new_f)),
+              "new_fwd_fps": 1000.0 / float(np.mean(new_f)),
+              "R_min": min(v["R"] for v in views), "R_max": max(v["R"] for v in views),
+              "max_tile_max": max(v["max_tile"] for v in views),
+              "new_fwdbwd_ms_mean": float(np.mean([v["new_fwdbwd_ms"] for v in views if "new_fwdbwd_ms" in v])),
+              "per_view": views}
+        if ref_f:
+            c5["gpu_reference_fwd_ms_mean"] = float(np.mean(ref_f))
+            c5["gpu_reference_fwdbwd_ms_mean"] = float(np.mean([v["gpu_reference_fwdbwd_ms"] for v in views
+                                                                if "gpu_reference_fwdbwd_ms" in v]))
+            c5["fwd_speedup_vs_gpu_reference"] = c5["gpu_reference_fwd_ms_mean"] / c5["new_fwd_ms_mean"]
+            c5["fwdbwd_speedup_vs_gpu_reference"] = c5["gpu_reference_fwdbwd_ms_mean"] / c5["new_fwdbwd_ms_mean"]
+        out["config5"] = c5
+        del t, dpix
+
+        # ---- simple-knn ----
+        rk = ref_loader.ref_knn()
+        kn = {}
+        for n in (65536, 100000, 500000):
+            pts = torch.from_numpy(scenes.head_points(np.random.default_rng(n), n).astype(np.float32)).to(dev)
+            e = {"new_ms": ev_ms(lambda: fknn.distCUDA2(pts), warm=3, iters=10)}
+            if rk is not None:
+                e["gpu_reference_ms"] = wall_ms(lambda: rk.distCUDA2(pts), warm=2, iters=5)
+                e["speedup_vs_gpu_reference"] = e["gpu_reference_ms"] / e["new_ms"]
+            kn[str(n)] = e
+        out["knn"] = kn
+    finally:
+        R.set_async(False)
+        di = dev.index
+        try:
+            R._drain_pending(R._pinned_slots(di), di, block=True)
+        except Exception as ex:
+            out["overflow"] = repr(ex)[:200]
+    return out
 
 
 def bench_config3(args, model, host, dev, avatar, torch, types):
@@ -654,6 +817,13 @@ def main():
         except Exception as ex:  # never let an extra key break the contract line
             config3 = {"error": repr(ex)[:300]}
 
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
+            extras = bench_extras(args, dev, torch)
+        except Exception as ex:
+            extras = {"error": repr(ex)[:300]}
+
     # ---- the reference's own CUDA rasterizer on the same GPU / frames (extra, rank 0) ----------------------
     gpu_ref = None
     if rank == 0:
@@ -746,7 +916,7 @@ def main():
                 "gpu_launches": launches[0] * args.steps, "gpu_launches_per_step": launches[0],
                 "step_issue": "one CUDA-graph launch per step" if use_graph else "eager C-ABI calls",
                 "exchange_check": exchange_check, "exchange_timing": exchange_timing, "roofline": roofline,
-                "kernels": kernels, "cpu_baseline": cb, "gpu_reference": gpu_ref, "config3": config3,
+                "kernels": kernels, "cpu_baseline": cb, "gpu_reference": gpu_ref, "config3": config3, "extras": extras,
                 "speedup_vs_gpu_reference": (value / world / gpu_ref["value"]) if gpu_ref and "value" in gpu_ref else None}
         print(json.dumps(line), file=REAL_STDOUT, flush=True)
     if dist is not None:
