@@ -12,7 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
-OUT = os.path.join(OUT_DIR, "libfatesplat.so")
+# FATESPLAT_BUILD_OUT: developer knob -- build an experiment variant next to the product library (see FATESPLAT_LIB)
+OUT = os.environ.get("FATESPLAT_BUILD_OUT") or os.path.join(OUT_DIR, "libfatesplat.so")
 SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "blend_forward.cu", "backward.cu", "knn.cu", "pose.cu", "flame.cu", "stats.cu", "exchange.cu", "optim.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "fatesplat.h")]
 

@@ -30,6 +30,7 @@ int fs_launch_knn(int P, const float* points, float* out, char* ws, size_t ws_by
 static thread_local char g_err[512] = "";
 static thread_local int g_launches = 0;
 static thread_local uint32_t g_tile_hint = 0;
+static thread_local int g_early_notify = 1;
 uint32_t fs_tile_hint() { return g_tile_hint; }
 
 void fs_set_error(const char* fmt, ...) {
@@ -232,7 +233,7 @@ int fs_forward(int P, int D, int M, const float* d_background, int width, int he
     // If h_info is pinned memory the device can address, the scan kernel also stores R / overflow there directly
     // (early notification); the full header is still copied at the end of the frame.
     fs_frame_info* h_info_dev = nullptr;
-    if (h_info) {
+    if (h_info && g_early_notify) {
         cudaPointerAttributes attr;
         if (cudaPointerGetAttributes(&attr, h_info) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
             attr.devicePointer != nullptr)
@@ -323,6 +324,7 @@ int fs_knn_mean_dist2(int P, const float* d_points, float* d_mean_dist2, void* d
 }
 
 void fs_set_tile_hint(uint32_t max_tile_instances) { g_tile_hint = max_tile_instances; }
+void fs_set_early_notify(int on) { g_early_notify = on != 0; }
 
 void fs_profile_enable(int on) { g_prof_on = on != 0; }
 

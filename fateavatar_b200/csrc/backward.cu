@@ -65,7 +65,10 @@ struct WarpStage {
 // back-to-front walk at its own segment instead of at the end of the list.  This bounds the serial chain of a
 // unit (the critical path when a dense tile's whole list belonged to one warp) and multiplies the number of
 // units available to keep every SM sub-partition busy.
-__global__ void __launch_bounds__(kWarps * 32)
+#ifndef FS_BWD_MIN_CTAS
+#define FS_BWD_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(kWarps * 32, FS_BWD_MIN_CTAS)
 blend_backward_kernel(const uint4* __restrict__ tile_meta, const uint2* __restrict__ seg_info,
                       const float4* __restrict__ ckpt,
                       const float4* __restrict__ final_C,

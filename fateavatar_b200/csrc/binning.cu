@@ -355,15 +355,20 @@ __device__ __forceinline__ void emit_sorted(const u64* keys, uint32_t n, uint32_
 }
 
 // ---- K4: one CTA per tile, segments of up to FS_SORT_SMEM_CAP keys -----------------------------------------
-constexpr int kSortThreads = 256;
+#ifndef FS_SORT_THREADS
+#define FS_SORT_THREADS 512
+#endif
+constexpr int kSortThreads = FS_SORT_THREADS;
 constexpr int kSortPer = FS_SORT_SMEM_CAP / kSortThreads;
+constexpr size_t kSortSmemBytes = (size_t)FS_SORT_SMEM_CAP * 16 + (FS_SORT_SMEM_CAP + 1) * 4 + 12;
 __global__ void __launch_bounds__(kSortThreads)
 tile_sort_kernel(const uint2* __restrict__ ranges, u64* __restrict__ keys, const float4* __restrict__ splat,
                  uint32_t* __restrict__ point_list, float4* __restrict__ inst_splat, uint32_t Rcap,
                  int big_kernel_follows) {
-    __shared__ u64 s_grp[FS_SORT_SMEM_CAP];
-    __shared__ u64 s_out[FS_SORT_SMEM_CAP];
-    __shared__ uint32_t s_cnt[FS_SORT_SMEM_CAP + 1];
+    extern __shared__ __align__(16) u64 s_sort[];
+    u64* s_grp = s_sort;
+    u64* s_out = s_sort + FS_SORT_SMEM_CAP;
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_sort + 2 * FS_SORT_SMEM_CAP);
     __shared__ uint32_t s_red[2 * (kSortThreads / 32)];
     fs::pdl_trigger();
     fs::pdl_wait();
@@ -461,7 +466,10 @@ void fs_launch_binning(int P, int W, int H, char* ws, const fs_workspace_layout&
     }
     {
         FsStageTimer t(FS_STAGE_TILE_SORT, stream);
-        fs_launch_pdl(tile_sort_kernel, dim3(Tn), dim3(kSortThreads), 0, stream, ranges, keys, splat, point_list,
+        static std::atomic<unsigned long long> sort_attr_set{0};
+        if (fs_first_use_on_device(sort_attr_set))
+            cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmemBytes);
+        fs_launch_pdl(tile_sort_kernel, dim3(Tn), dim3(kSortThreads), kSortSmemBytes, stream, ranges, keys, splat, point_list,
                       inst_splat, Rcap, launch_big ? 1 : 0);
     }
     if (!launch_big) {

@@ -215,6 +215,8 @@ inline cudaError_t fs_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-#define FS_SORT_SMEM_CAP 2048  // instances a tile may hold to be sorted by the one-CTA-per-tile kernel
+#ifndef FS_SORT_SMEM_CAP
+#define FS_SORT_SMEM_CAP 4096  // instances a tile may hold to be sorted by the one-CTA-per-tile kernel
+#endif
 // Per-tile counters live 128 bytes apart: L2 atomics to one line serialise, and only a few hundred tiles are hot.
 #define FS_CNT_STRIDE 32

@@ -258,6 +258,7 @@ def forward_raw(raster_settings, means3D, sh, colors_precomp, opacities, scales,
             if own_ws is not None:
                 capacity = _capacity_for_bytes(lib, P, W, H, own_ws)
             lib.fs_set_tile_hint(int(_tile_hint.get(key, 0) * 1.25))
+            lib.fs_set_early_notify(0 if (_ASYNC or capturing) else 1)  # nobody polls R in the no-host-sync modes
             while capturing:
                 # CUDA-graph capture (fateavatar_b200.graph): the launches are recorded, not run, so nothing can be
                 # waited for.  The frame gets a generous fixed capacity and its own pinned header, which every

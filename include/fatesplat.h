@@ -127,6 +127,11 @@ int fs_backward(int P, int D, int M, const float* d_background, int width, int h
  * are launched, never the result.
  */
 void fs_set_tile_hint(uint32_t max_tile_instances);
+/* Per calling thread (default on): when h_info is pinned host memory, fs_forward's scan kernel also stores R / overflow
+ * straight into it (zero-copy store + system fence) long before the frame ends, for callers that block on R like the
+ * reference (rasterizer_impl.cu:281).  Callers that never wait (no-host-sync mode, CUDA-graph replay) switch it off and
+ * save the kernel that fence; the full header is still copied to h_info at the end of the frame. */
+void fs_set_early_notify(int on);
 
 /* present[i] = (view-space z of means3D[i] > 0.2); uint8 0/1 (rasterizer_impl.cu:54-66). */
 int fs_mark_visible(int P, const float* d_means3D, const float* d_viewmatrix, const float* d_projmatrix,
