@@ -469,7 +469,7 @@ def main():
     import numpy as np
     import torch
 
-    from fateavatar_b200 import _lib, avatar, flame, parallel, rasterizer as R
+    from fateavatar_b200 import _lib, avatar, flame, losses, parallel, rasterizer as R
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl new needs a CUDA device (no CPU fallback exists)")
@@ -628,6 +628,11 @@ def main():
     barrier()
     sampler.stop_flag = True
     total_ms = e0.elapsed_time(e1)
+    if os.environ.get("FATESPLAT_BENCH_PROFILE") == "value":  # ncu --profile-from-start off: two steps of the timed loop
+        torch.cuda.profiler.start()
+        run(0), run(1)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     di = dev.index
     exchange_timing = None
     if sharded is not None and sharded.ex is not None:
@@ -730,8 +735,8 @@ def main():
     def frame_loss(m, d):
         """One training frame through the public API; `d` holds this frame's inputs on the device."""
         out = avatar.forward_frame(m, dict(cam_pose=d["cam_pose"], fovx=fov, fovy=fov, flame_pose=d["flame_pose"],
-                                           expression=d["expression"]))
-        return (out["rgb_image"][0] - d["target"]).abs().mean(), out
+                                           expression=d["expression"]), extras=False)  # the L1 loss reads the image only
+        return losses.l1_image_loss(out["rgb_image"][0], d["target"]), out
 
     def eager_step(i):  # every operator call issued from Python, default synchronous mode
         h = host[i % N_RING]
@@ -751,11 +756,12 @@ def main():
         return float(out_loss[0])
 
     def time_e2e(fn, n):
-        for i in range(max(5, n_warm)):
+        w = max(5, n_warm)
+        for i in range(w):
             fn(i)
         barrier()
         e0.record()
-        for i in range(n):
+        for i in range(w, w + n):  # (the step counter keeps running: consecutive steps alternate recordings / buckets)
             fn(i)
         e1.record()
         barrier()
@@ -775,14 +781,22 @@ def main():
         e2e_sharded.capture(frame_loss, {k: v.to(dev) for k, v in host[0].items()})
         barrier()
 
+        e2e_sharded.prefetch(0, host[0])
+        pipe = {"prev": None, "losses": []}
+
         def graph_step(i):
-            out = e2e_sharded(i, host[i % N_RING])
-            e2e_sharded.wait()
-            return float(out["loss"][0])
+            e2e_sharded(i)                                    # waits for the staged inputs of step i, one graph launch
+            e2e_sharded.prefetch(i + 1, host[(i + 1) % N_RING])  # H2D of the next frame overlaps this step
+            if pipe["prev"] is not None:                      # the loss of step i-1 is read while step i runs: every
+                out = e2e_sharded.wait(pipe["prev"])          # step's result reaches the host, the GPU never idles
+                pipe["losses"].append(float(out["loss"][0]))
+            pipe["prev"] = i
         api = ("fateavatar_b200.parallel.ShardedStep (captured): avatar.forward_frame (the mirror of FateAvatar.forward: "
                "camera, FLAME skinning, splat placement, GaussianRasterizer) + L1 loss + backward under autograd, gradient "
                "pack and the fused peer-memory exchange, replayed as one CUDA graph per step; host inputs (expression, "
-               "pose, camera pose, target image) copied in and the loss copied out through pinned memory every step")
+               "pose, camera pose, target image) copied in from pinned memory every step -- the copy of frame i+1 is issued on a "
+               "side stream right after the launch of step i -- and the loss copied out (D2H inside the graph) and read by the "
+               "host every step, one step behind the launches so that the GPU does not idle between steps")
     else:
         from fateavatar_b200 import graph as fgraph
 
@@ -798,6 +812,15 @@ def main():
         api = "graph.CapturedStep replaying avatar.forward_frame + L1 loss + backward; dense NCCL all-reduce per leaf"
 
     graph_fps = time_e2e(graph_step, e2e_steps)
+    if os.environ.get("FATESPLAT_BENCH_PROFILE") == "e2e":  # ncu --profile-from-start off: two replays of the e2e step
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        for i in range(1000, 1002):
+            graph_step(i)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+    if e2e_sharded is not None:
+        assert len(pipe["losses"]) >= e2e_steps and all(np.isfinite(pipe["losses"])), "e2e: every step's loss must arrive"
     R.set_async(False)
     e2e = {"value": graph_fps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
            "api": api, "eager_value": eager_fps,

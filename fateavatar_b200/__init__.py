@@ -10,6 +10,7 @@ mirrors of the reference's interfaces for that path:
     densify.py              _add_densification_stats                                         (fs_densify_stats)
     avatar.py               FateAvatar.forward as one call (forward_frame / attach)
     graph.py                whole-frame CUDA-graph capture / replay (CapturedStep)
+    optimizer.py, losses.py   optimise loop: fused Adam, in-place densify / prune / reset, OptimiseLoop; fused L1 image loss
     exchange.py, parallel.py  frame-sharded multi-GPU: peer-memory gradient exchange, sampler, densify sync
 
     import fateavatar_b200; fateavatar_b200.install()

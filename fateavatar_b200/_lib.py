@@ -40,7 +40,8 @@ EXPORTS = [
     "fs_knn_workspace_bytes", "fs_knn_mean_dist2", "fs_last_launch_count", "fs_last_error", "fs_version",
     "fs_profile_enable", "fs_profile_read", "fs_pose_forward", "fs_pose_backward", "fs_set_tile_hint",
     "fs_flame_workspace_bytes", "fs_flame_forward", "fs_flame_backward", "fs_flame_backward_coeffs", "fs_densify_stats", "fs_flame_expand_grads", "fs_p2p_allreduce", "fs_p2p_reduce_scatter_bcast",
-    "fs_p2p_exchange", "fs_p2p_wait", "fs_p2p_exchange_flag_floats", "fs_densify_stats_inc", "fs_p2p_exchange_timing", "fs_set_early_notify",
+    "fs_p2p_exchange", "fs_p2p_wait", "fs_p2p_exchange_flag_floats", "fs_densify_stats_inc", "fs_p2p_exchange_timing", "fs_set_early_notify", "fs_frame_camera", "fs_l1_loss", "fs_l1_loss_workspace_bytes",
+    "fs_adam_step", "fs_splat_append", "fs_splat_prune_workspace_bytes", "fs_splat_prune", "fs_opacity_reset",
 ]
 
 STAGES = ["preprocess", "tile_scan", "scatter", "tile_sort", "big_tile_sort", "blend_forward", "blend_backward",
@@ -111,6 +112,12 @@ def load():
     lib.fs_densify_stats_inc.argtypes = [i, vp, vp, vp, vp, vp]
     lib.fs_densify_stats.restype = i
     lib.fs_densify_stats.argtypes = [i, vp, vp, vp, vp, vp]
+    lib.fs_l1_loss_workspace_bytes.restype = sz
+    lib.fs_l1_loss_workspace_bytes.argtypes = []
+    lib.fs_l1_loss.restype = i
+    lib.fs_l1_loss.argtypes = [sz, vp, vp, vp, vp, vp, vp]
+    lib.fs_frame_camera.restype = i
+    lib.fs_frame_camera.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.fs_set_early_notify.restype = None
     lib.fs_set_early_notify.argtypes = [i]
     lib.fs_set_tile_hint.restype = None

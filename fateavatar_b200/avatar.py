@@ -34,7 +34,7 @@ class FrameCamera:
     _proj_cache = {}
     _const_cache = {}
 
-    def __init__(self, R, T, FoVx, FoVy, img_res, znear=0.01, zfar=100.0, exact=False):
+    def __init__(self, R, T, FoVx, FoVy, img_res, znear=0.01, zfar=100.0, exact=False, cam_pose=None):
         """exact=True runs the reference's own sequence of library calls instead of the closed form -- Rt assembled on
         the host, torch.linalg.inv twice on the CPU (tools/gs_utils/graphics_utils.py:51-62), upload, bmm, and the GPU
         inverse for the camera centre (volume_rendering/camera_3dgs.py:53,71-72) -- so that view / projection matrices
@@ -57,6 +57,20 @@ class FrameCamera:
             self.world_view_transform, self.projection_matrix = view, proj
             self.full_proj_transform = view.unsqueeze(0).bmm(proj.unsqueeze(0)).squeeze(0)
             self.camera_center = view.inverse()[3, :3]
+            return
+        if cam_pose is not None and cam_pose.is_cuda and cam_pose.dtype == torch.float32 and cam_pose.numel() == 16:
+            # one kernel (fs_frame_camera) instead of ~8 small torch launches per frame
+            from . import _lib
+
+            cp = cam_pose.reshape(4, 4).contiguous()
+            proj = self._projection(dev)
+            buf = torch.empty(36, device=dev)
+            with _lib.on_device(dev):
+                rc = _lib.load().fs_frame_camera(cp.data_ptr(), proj.data_ptr(), buf.data_ptr(), buf.data_ptr() + 64,
+                                                 buf.data_ptr() + 128, _lib.stream_ptr(dev))
+            _lib.check(rc, "fs_frame_camera")
+            self.world_view_transform, self.full_proj_transform = buf[:16].view(4, 4), buf[16:32].view(4, 4)
+            self.projection_matrix, self.camera_center = proj, buf[32:35]
             return
         consts = FrameCamera._const_cache.get(str(dev))
         if consts is None:  # built once per device, outside any CUDA-graph capture (warm-up frames come first)
@@ -104,8 +118,11 @@ def quaternion_to_axis_angle(q):
     return q[..., 1:] / s
 
 
-def forward_frame(model, input, exact_camera=None):
+def forward_frame(model, input, exact_camera=None, extras=True):
     """`exact_camera` (default: `model.exact_camera` if set, else False) selects FrameCamera(exact=True).
+    `extras=False` leaves out the two outputs that only the scale / rotation regularisers read ("scale" = exp(_scaling),
+    "raw_rot" = quaternion_to_axis_angle(_rotation): ~15 elementwise launches per frame) for callers whose loss does not
+    use them; everything else is computed regardless.
     `model`: an object with FateAvatar's attributes (flame, faces, face_index, bary_coords, face_scaling_canonical,
     _scaling, _rotation, _offset, _opacity, _features_dc, delta_shapedirs, delta_posedirs, delta_vertex, cfg_model,
     shell_len, bg_color, img_res, device); `input`: the dataset's dict (cam_pose, fovx, fovy, flame_pose, expression).
@@ -114,7 +131,7 @@ def forward_frame(model, input, exact_camera=None):
     if exact_camera is None:
         exact_camera = bool(getattr(model, "exact_camera", False))
     camera = FrameCamera(cam_pose[:, :3, :3], cam_pose[:, :3, 3], input["fovx"][0], input["fovy"][0], model.img_res,
-                         exact=exact_camera)
+                         exact=exact_camera, cam_pose=None if exact_camera else cam_pose)
     flame_pose, expression = input["flame_pose"], input["expression"]
     bs = flame_pose.shape[0]
     if bs != 1:
@@ -142,10 +159,9 @@ def forward_frame(model, input, exact_camera=None):
         campos=camera.camera_center, prefiltered=False, debug=False)
     image, radii = _rasterizer.GaussianRasterizer(settings)(means3D=xyz, means2D=screenspace, shs=model._features_dc,
                                                            opacities=opac, scales=scales, rotations=rots)
-    return {
+    out = {"scale": torch.exp(model._scaling), "raw_rot": quaternion_to_axis_angle(model._rotation)} if extras else {}
+    out.update({
         "rgb_image": image[None],
-        "scale": torch.exp(model._scaling),
-        "raw_rot": quaternion_to_axis_angle(model._rotation),
         "viewspace_points": [screenspace],
         "visibility_filter": [radii > 0],
         "radii": [radii],
@@ -153,7 +169,8 @@ def forward_frame(model, input, exact_camera=None):
         "verts": verts,
         "verts_orig": verts_orig,
         "faces": model.faces,
-    }
+    })
+    return out
 
 
 def attach(model, exact_camera=False):

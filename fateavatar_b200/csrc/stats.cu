@@ -2,6 +2,8 @@
 // 418-420):   xyz_gradient_accum[filter] += ||viewspace.grad[filter, :2]||;   denom[filter] += 1
 // Upstream this is boolean-mask indexing (nonzero + gather + norm + index_put, a host sync among them); here it is
 // one masked elementwise pass over 16 bytes per splat, no synchronisation.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -27,6 +29,109 @@ densify_stats_inc_kernel(int P, const float* __restrict__ grad2d, const int* __r
     denom_inc[i] = vis ? 1.0f : 0.0f;
 }
 }  // namespace
+
+// ---- per-frame camera ---------------------------------------------------------------------------------
+// volume_rendering/camera_3dgs.py:53-72 builds the view matrix through two CPU 4x4 inverses, a host round trip and a GPU
+// inverse per frame; in closed form  world_view = [[R, 0], [T, 1]],  full = world_view * P^T,  centre = -R T  it is 35
+// floats of arithmetic: one warp, no host involvement, CUDA-graph capturable.
+static __global__ void frame_camera_kernel(const float* __restrict__ cam_pose, const float* __restrict__ proj_t,
+                                    float* __restrict__ view, float* __restrict__ full, float* __restrict__ campos) {
+    __shared__ float v[16];
+    const int t = threadIdx.x;
+    if (t < 16) {
+        const int i = t >> 2, j = t & 3;
+        float x;
+        if (i < 3) x = j < 3 ? cam_pose[4 * i + j] : 0.0f;        // R (camera-to-world rotation as cam_pose holds it)
+        else x = j < 3 ? cam_pose[4 * j + 3] : 1.0f;              // T (world-to-camera translation)
+        v[t] = x;
+        view[t] = x;
+    }
+    __syncthreads();
+    if (t < 16) {
+        const int i = t >> 2, j = t & 3;
+        float acc = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc = fmaf(v[4 * i + k], proj_t[4 * k + j], acc);
+        full[t] = acc;
+    } else if (t < 19) {
+        const int i = t - 16;
+        campos[i] = -(v[4 * i] * v[12] + v[4 * i + 1] * v[13] + v[4 * i + 2] * v[14]);
+    }
+}
+
+extern "C" int fs_frame_camera(const float* d_cam_pose, const float* d_projection_t, float* d_world_view,
+                               float* d_full_proj, float* d_camera_center, void* stream) {
+    if (!d_cam_pose || !d_projection_t || !d_world_view || !d_full_proj || !d_camera_center) {
+        fs_set_error("fs_frame_camera: required pointer is NULL");
+        return FS_ERR_INVALID_ARGUMENT;
+    }
+    frame_camera_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(d_cam_pose, d_projection_t, d_world_view,
+                                                                        d_full_proj, d_camera_center);
+    fs_count_launch(1);
+    if (cudaGetLastError() != cudaSuccess) {
+        fs_set_error("fs_frame_camera: launch failed");
+        return FS_ERR_CUDA;
+    }
+    return FS_OK;
+}
+
+// ---- fused L1 image loss (training-loop plumbing) -------------------------------------------------------
+// train/loss.py:103-105 (rgb_type 'l1'): loss = mean |x - t|.  As torch ops the forward and backward are ~9 launches over
+// the 3 MB image (sub, abs, mean, fill, div, sign, mul, ...); here ONE pass writes the loss and d loss / d x =
+// sign(x - t) / n.  Deterministic: per-CTA partial sums are added in CTA order by the last CTA to finish.
+constexpr int kL1Threads = 256;
+static __global__ void __launch_bounds__(kL1Threads)
+l1_loss_kernel(size_t n, const float* __restrict__ x, const float* __restrict__ t, float* __restrict__ grad,
+               float* __restrict__ partial, unsigned int* __restrict__ counter, float* __restrict__ loss) {
+    __shared__ float s_w[kL1Threads / 32];
+    __shared__ bool s_last;
+    const float inv_n = 1.0f / (float)n;
+    float acc = 0.0f;
+    for (size_t i = (size_t)blockIdx.x * kL1Threads + threadIdx.x; i < n; i += (size_t)gridDim.x * kL1Threads) {
+        const float d = x[i] - t[i];
+        acc += fabsf(d);
+        grad[i] = d > 0.0f ? inv_n : (d < 0.0f ? -inv_n : 0.0f);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float b = 0.0f;
+        for (int w = 0; w < kL1Threads / 32; ++w) b += s_w[w];
+        partial[blockIdx.x] = b;
+        __threadfence();
+        s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        float total = 0.0f;
+        for (unsigned int b = 0; b < gridDim.x; ++b) total += *reinterpret_cast<volatile float*>(partial + b);
+        *loss = total * inv_n;
+        *counter = 0u;
+    }
+}
+
+extern "C" size_t fs_l1_loss_workspace_bytes(void) { return 1024 * sizeof(float) + 256; }
+
+extern "C" int fs_l1_loss(size_t n, const float* d_x, const float* d_target, float* d_grad, float* d_loss,
+                          void* d_workspace, void* stream) {
+    if (n == 0 || !d_x || !d_target || !d_grad || !d_loss || !d_workspace) {
+        fs_set_error("fs_l1_loss: invalid argument");
+        return FS_ERR_INVALID_ARGUMENT;
+    }
+    const int grid = (int)std::min<size_t>((n + kL1Threads * 4 - 1) / (kL1Threads * 4), 1024);
+    float* partial = static_cast<float*>(d_workspace);
+    unsigned int* counter = reinterpret_cast<unsigned int*>(partial + 1024);  // zero-initialised by the caller once
+    l1_loss_kernel<<<grid, kL1Threads, 0, static_cast<cudaStream_t>(stream)>>>(n, d_x, d_target, d_grad, partial, counter,
+                                                                               d_loss);
+    fs_count_launch(1);
+    if (cudaGetLastError() != cudaSuccess) {
+        fs_set_error("fs_l1_loss: launch failed");
+        return FS_ERR_CUDA;
+    }
+    return FS_OK;
+}
 
 extern "C" int fs_densify_stats_inc(int P, const float* d_viewspace_grad, const int* d_radii, float* d_accum_inc,
                                     float* d_denom_inc, void* stream) {

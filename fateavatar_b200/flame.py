@@ -146,6 +146,7 @@ class _FlameLBS(torch.autograd.Function):
         if want_orig:
             outs += (r["verts_orig"], r["transforms_orig"])
         ctx.mark_non_differentiable(*outs[1:])
+        ctx.set_materialize_grads(False)  # no zero-filled gradients for the four by-products on every backward
         return outs
 
     @staticmethod
@@ -205,6 +206,12 @@ def flame_lbs(model, betas, pose, delta_shapedirs=None, delta_posedirs=None, del
     if betas.dim() == 2 and betas.shape[0] != 1:
         raise FateSplatError("flame_lbs handles one frame per call (the reference's batch size); loop over frames")
     outs = _FlameLBS.apply(betas, pose, delta_vertex, delta_shapedirs, delta_posedirs, model, int(l0), bool(want_orig))
+    if want_orig and (betas.requires_grad or pose.requires_grad):
+        # Per-frame tracking optimisation (train/base.py:113-151): upstream's flame.forward(expression, pose) is
+        # differentiable w.r.t. the coefficients (flame_loss = (verts - verts_orig)^2, train/loss.py:197-201), the
+        # by-product of the fused pass is not -- so the undeformed mesh gets its own differentiable pass here.
+        o2 = _FlameLBS.apply(betas, pose, None, None, None, model, int(l0), False)
+        outs = (outs[0], outs[1], outs[2], o2[0], o2[2])
     return tuple(o[None] for o in outs)
 
 
@@ -221,18 +228,23 @@ def attach(flame_module):
         return torch.cat([torch.zeros(e.shape[0], n_shape, device=e.device, dtype=e.dtype), e], dim=1)
 
     def key_of(expression_params, full_pose):
-        return (expression_params.data_ptr(), expression_params._version, full_pose.data_ptr(), full_pose._version)
+        # the entry keeps strong references to the two tensors, so neither address can be recycled while it is cached
+        return (expression_params, expression_params._version, full_pose, full_pose._version)
+
+    def same(a, b):
+        return a is not None and a[0] is b[0] and a[1] == b[1] and a[2] is b[2] and a[3] == b[3]
 
     def forward_with_delta_blendshape(expression_params, full_pose, delta_shapedirs=None, delta_posedirs=None,
                                       delta_vertex=None):
         v, pf, A, vo, Ao = flame_lbs(model, betas_of(expression_params), full_pose, delta_shapedirs, delta_posedirs,
                                      delta_vertex, l0=n_shape, want_orig=True)
         cache.clear()
-        cache[key_of(expression_params, full_pose)] = (vo, pf, Ao)
+        cache["key"], cache["val"] = key_of(expression_params, full_pose), (vo, pf, Ao)
         return v, pf, A
 
     def forward(expression_params, full_pose):
-        hit = cache.pop(key_of(expression_params, full_pose), None)
+        hit = cache.get("val") if same(cache.get("key"), key_of(expression_params, full_pose)) else None
+        cache.clear()
         if hit is not None:
             return hit
         v, pf, A = flame_lbs(model, betas_of(expression_params), full_pose, l0=n_shape, want_orig=False)

@@ -27,6 +27,8 @@ class CapturedStep:
     def __init__(self, frame_fn, example_inputs, params=(), warmup=3, device=None, on_capture=None):
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         dev = self.device
+        self._staged = None
+        self._done = torch.cuda.Event()
         self.params = list(params)
         self.static_in = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in example_inputs.items()}
         for k, v in example_inputs.items():
@@ -68,16 +70,35 @@ class CapturedStep:
         self.headers = _R.capture_headers[n0:]
         del _R.capture_headers[n0:]
 
-    def __call__(self, host_inputs):
+    def __call__(self, host_inputs=None):
         """Copy this frame's inputs in (asynchronously, from pinned host tensors), replay, return the pinned outputs
-        (valid after `wait()`)."""
-        for k, v in host_inputs.items():
-            self.static_in[k].copy_(v, non_blocking=True)
+        (valid after `wait()`).  With host_inputs=None the inputs staged by `prefetch()` are used."""
+        if host_inputs is not None:
+            for k, v in host_inputs.items():
+                self.static_in[k].copy_(v, non_blocking=True)
+        elif self._staged is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._staged)
+            self._staged = None
         self.graph.replay()
+        self._done.record(torch.cuda.current_stream(self.device))
         return self.host_out
 
+    def prefetch(self, host_inputs, stream):
+        """Input prefetch (the pinned GT-frame prefetch of SURVEY 8f N3; upstream loads every frame synchronously,
+        train/dataset.py:14-54): copy the NEXT frame's pinned host inputs into this step's static input tensors on
+        `stream` while another recorded step is still running.  The caller guarantees that this step is not in
+        flight (steps alternate between two recordings and each is waited for before it is reused)."""
+        with torch.cuda.stream(stream):
+            for k, v in host_inputs.items():
+                self.static_in[k].copy_(v, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        self._staged = ev
+
     def wait(self):
-        torch.cuda.current_stream(self.device).synchronize()
+        """Block until THIS recording's last replay has finished (later launches on the stream keep running), check it
+        for workspace overflow and return its pinned outputs."""
+        self._done.synchronize()
         self.check()
         return self.host_out
 

@@ -285,13 +285,23 @@ class ShardedStep:
                           for k in (0, 1)]
         return self
 
-    def __call__(self, step, host_inputs):
+    def __call__(self, step, host_inputs=None):
+        """Replay step `step` on `host_inputs` (copied in first) or, with None, on the inputs `prefetch` staged for it."""
         c = self._captured[step & 1]
         self._last = c
         return c(host_inputs)
 
-    def wait(self):
-        return self._last.wait()
+    def prefetch(self, step, host_inputs):
+        """Stage the pinned host inputs of a FUTURE step (normally step + 1, issued right after the launch of `step`) on a
+        side stream, so that the H2D copy overlaps the running step instead of preceding the next one."""
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        self._captured[step & 1].prefetch(host_inputs, self._copy_stream)
+
+    def wait(self, step=None):
+        """Outputs of the last launched step (or of `step`): blocks only until THAT step has finished, so a caller may
+        launch step s + 1 first and read step s afterwards -- the GPU then never idles between steps."""
+        return (self._last if step is None else self._captured[step & 1]).wait()
 
     def grads(self, step):
         """After capture(): the gradient dict the replay of `step` refreshes (fixed tensors per parity)."""

@@ -390,10 +390,13 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.num_rendered = state["num_rendered"]
         ctx.save_for_backward(*state["tensors"])
         ctx.mark_non_differentiable(radii)
+        ctx.set_materialize_grads(False)  # no zero-filled "gradient" of radii on every backward
         return color, radii
 
     @staticmethod
     def backward(ctx, grad_out_color, _):
+        if grad_out_color is None:
+            return (None,) * 9
         state = dict(ctx.state)
         state["tensors"] = ctx.saved_tensors
         P, D, M, H, W = state["dims"]

@@ -288,6 +288,18 @@ int fs_p2p_exchange_timing(float* d_local_base, size_t flags_offset, double* wai
  */
 int fs_densify_stats(int P, const float* d_viewspace_grad, const uint8_t* d_update_filter,
                      float* d_xyz_gradient_accum, float* d_denom, void* stream);
+/* Per-frame camera in closed form (replaces the two CPU inverses, the host round trip and the GPU inverse
+ * of volume_rendering/camera_3dgs.py:53-72): d_cam_pose [4,4] row-major as the dataset yields it (camera-to-world rotation
+ * in [:3,:3], world-to-camera translation in [:3,3]), d_projection_t = getProjectionMatrix(...)^T [4,4]  ->
+ * world_view_transform [4,4], full_proj_transform [4,4], camera_center [3].  One launch, no host involvement. */
+int fs_frame_camera(const float* d_cam_pose, const float* d_projection_t, float* d_world_view, float* d_full_proj,
+                    float* d_camera_center, void* stream);
+/* Fused L1 image loss of the optimise loop (train/loss.py:103-105, rgb_type 'l1'): *d_loss = mean |x - target| and
+ * d_grad[i] = sign(x[i] - target[i]) / n in ONE pass (as torch ops: ~9 launches over the image).  Deterministic.
+ * d_workspace: fs_l1_loss_workspace_bytes() bytes, zero-initialised once by the caller, reusable across calls. */
+size_t fs_l1_loss_workspace_bytes(void);
+int fs_l1_loss(size_t n, const float* d_x, const float* d_target, float* d_grad, float* d_loss, void* d_workspace,
+               void* stream);
 /* Frame-sharded form of the same statistic: this frame's increments, written (not accumulated) -- hypot(grad) and 1
  * where d_radii[i] > 0, else 0 -- so that they can travel in the gradient bucket and be summed over ranks. */
 int fs_densify_stats_inc(int P, const float* d_viewspace_grad, const int* d_radii, float* d_accum_inc,

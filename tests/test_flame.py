@@ -239,6 +239,44 @@ def test_expression_and_pose_coefficient_gradients(case, cuda_device):
 
 
 @pytest.mark.gpu
+def test_flame_loss_gradient_reaches_the_coefficients_through_verts_orig(cuda_device):
+    """train/loss.py:197-201: flame_loss = mean((verts - verts_orig)^2).  With per-frame tracking optimisation the
+    expression / pose coefficients require grad and upstream's flame.forward is differentiable w.r.t. them, so the
+    -d verts_orig / d(coefficients) term must be present: against float64 autograd of the oracle."""
+    from fateavatar_b200 import flame
+
+    f, l0 = scenes.flame_inputs(seed=21, V=300), 300
+    m64 = _model(f, torch.float64)
+    t64 = lambda k: torch.from_numpy(f[k]).double()
+    b64, p64 = t64("betas").requires_grad_(True), t64("pose").requires_grad_(True)
+    v64, _, _ = fo.forward_with_delta_blendshape(m64, b64, p64, t64("delta_shapedirs"), t64("delta_posedirs"), t64("delta_vertex"))
+    vo64, _, _ = fo.forward_with_delta_blendshape(m64, b64, p64)
+    ((v64 - vo64) ** 2).mean().backward()
+    want_b = b64.grad.numpy().copy()
+    want_b[:l0] = 0.0
+    m = _model(f, torch.float32, cuda_device)
+    m["parents"] = [int(x) for x in f["parents"]]
+    t = lambda k: torch.from_numpy(f[k]).to(cuda_device)
+    betas, pose = t("betas")[None].requires_grad_(True), t("pose")[None].requires_grad_(True)
+    outs = flame.flame_lbs(m, betas, pose, t("delta_shapedirs"), t("delta_posedirs"), t("delta_vertex"), l0=l0, want_orig=True)
+    ((outs[0] - outs[3]) ** 2).mean().backward()
+    got_b, got_p = betas.grad[0].cpu().numpy(), pose.grad[0].cpu().numpy()
+    assert np.abs(got_b - want_b).max() <= 1e-4 * np.abs(want_b).max(), (np.abs(got_b - want_b).max(), np.abs(want_b).max())
+    assert np.abs(got_p - p64.grad.numpy()).max() <= 1e-4 * np.abs(p64.grad.numpy()).max()
+    # and through the attached reference-style methods (cache hit path included)
+    mod = types.SimpleNamespace(n_shape=300, n_exp=100, parents=torch.from_numpy(f["parents"]),
+                                **{k: t(k) for k in ("v_template", "shapedirs", "posedirs", "J_regressor", "lbs_weights")})
+    flame.attach(mod)
+    expr = t("betas")[None, 300:].clone().requires_grad_(True)
+    pose2 = t("pose")[None].clone().requires_grad_(True)
+    v, _, _ = mod.forward_with_delta_blendshape(expr, pose2, t("delta_shapedirs"), t("delta_posedirs"), t("delta_vertex"))
+    vo, _, _ = mod.forward(expr, pose2)
+    ((v - vo) ** 2).mean().backward()
+    assert np.abs(expr.grad[0].cpu().numpy() - want_b[300:]).max() <= 1e-4 * np.abs(want_b).max()
+    assert np.abs(pose2.grad[0].cpu().numpy() - p64.grad.numpy()).max() <= 1e-4 * np.abs(p64.grad.numpy()).max()
+
+
+@pytest.mark.gpu
 def test_expand_factors_kernel_and_single_rank_identity(cuda_device):
     """fs_flame_expand_grads: (a) N = 3 random records vs the torch statement; (b) with N = 1 and this rank's own
     factors it reproduces the dense gradients fs_flame_backward writes (the rank-1 structure is exact)."""

@@ -17,6 +17,24 @@ HAVE_REF = os.path.isdir(H.STAGED)
 LRS = dict(fopt.OptimiseLoop.DEFAULTS)
 
 
+def test_fused_l1_image_loss_matches_torch(cuda_device):
+    from fateavatar_b200 import losses
+
+    g = torch.Generator(device=cuda_device).manual_seed(3)
+    for shape in ((3, 512, 512), (1, 3, 33, 47)):
+        x = torch.rand(shape, device=cuda_device, generator=g).requires_grad_(True)
+        t = torch.rand(shape, device=cuda_device, generator=g)
+        t.view(-1)[:5] = x.detach().view(-1)[:5]  # exact ties: sign(0) = 0 on both sides
+        (losses.l1_image_loss(x, t) * 1.7).backward()
+        got_g, x.grad = x.grad.clone(), None
+        ref = (x - t).abs().mean()
+        (ref * 1.7).backward()
+        assert abs(float(losses.l1_image_loss(x, t)) - float(ref)) <= 1e-6 * float(ref)
+        assert float((got_g - x.grad).abs().max()) <= 1e-7 * float(x.grad.abs().max())
+        a, b = losses.l1_image_loss(x, t), losses.l1_image_loss(x, t)
+        assert float(a) == float(b)  # deterministic
+
+
 def test_fused_adam_matches_torch_adam(cuda_device):
     dev = cuda_device
     g = torch.Generator(device=dev).manual_seed(0)
