@@ -131,36 +131,61 @@ def cpu_pose_and_render(f, dpix, orc, po, fo, torch):
 
 # ---------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """SM clock / throttle reasons sampled while the timed region runs.
+
+    NVML is opened in the constructor (nvmlInit takes tens of ms -- longer than a 20-step timed region), the thread
+    samples every 0.5 ms, and the timing loop also calls sample() itself while it waits for the end event, so even a
+    6 ms region is covered whatever the interpreter's thread switching does.  nvidia-smi is the fallback."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
-
-    def run(self):
-        try:  # NVML in-process: ~0.1 ms per sample, so even a short timed region is covered
+        self.index, self.rows, self.stop_flag, self.nv = index, [], False, None
+        try:
             import pynvml as nv
 
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
-                    "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
-            while not self.stop_flag:
-                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
-                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                row = [str(self.index), str(sm), str(mx), "", hex(r)]
-                row += ["Active" if (r & bits[k]) else "Not Active" for k in ("hw_slowdown", "hw_thermal_slowdown",
-                                                                              "sw_thermal_slowdown", "sw_power_cap")]
-                self.rows.append(row)
-                time.sleep(0.002)
-            return
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = index
+            if vis and all(t.strip().isdigit() for t in vis.split(",")) and index < len(vis.split(",")):
+                phys = int(vis.split(",")[index])
+            self.h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            self.bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                         "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                         "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                         "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+            self.nv = nv
+            self.sample()
+            self.rows.clear()
         except Exception:
-            pass
+            self.nv = None
+
+    def sample(self):
+        """One NVML sample (about 0.1 ms); no-op on the nvidia-smi fallback."""
+        nv = self.nv
+        if nv is None:
+            return
+        sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        row = [str(self.index), str(sm), str(self.mx), "", hex(r)]
+        row += ["Active" if (r & self.bits[k]) else "Not Active" for k in self.NAMES]
+        self.rows.append(row)
+
+    def run(self):
+        if self.nv is not None:
+            while not self.stop_flag:
+                try:
+                    self.sample()
+                except Exception:
+                    break
+                time.sleep(0.0005)
+            if self.stop_flag:
+                return
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
@@ -625,6 +650,8 @@ def main():
     for i in range(args.steps):
         run(i)
     e1.record()
+    while not e1.query():  # the launches are queued far ahead of the device: sample the clocks while it works
+        sampler.sample()
     barrier()
     sampler.stop_flag = True
     total_ms = e0.elapsed_time(e1)

@@ -27,7 +27,10 @@ namespace {
 constexpr int kWarps = 8;     // warps per CTA (independent; they only share the CTA's shared memory)
 constexpr int kBatch = 64;    // records per stage
 constexpr int kStages = 2;
-constexpr int kGroup = 4;
+#ifndef FS_FWD_GROUP
+#define FS_FWD_GROUP 4
+#endif
+constexpr int kGroup = FS_FWD_GROUP;
 
 struct WarpStage {
     SplatRec rec[kStages][kBatch];
@@ -195,9 +198,10 @@ blend_forward_kernel(const uint4* __restrict__ tile_meta, const uint32_t* __rest
                 while (m) {
                     Group g;
                     compute_group(g, m, c, rec, pxf, pyf);
-                    if (!__any_sync(0xffffffffu, (g.alpha[0] >= 0.0f) | (g.alpha[1] >= 0.0f) | (g.alpha[2] >= 0.0f) |
-                                                     (g.alpha[3] >= 0.0f)))
-                        continue;
+                    bool any_a = false;
+#pragma unroll
+                    for (int k = 0; k < kGroup; ++k) any_a |= g.alpha[k] >= 0.0f;
+                    if (!__any_sync(0xffffffffu, any_a)) continue;
                     apply_group(g, (uint32_t)b * kBatch, T, C0, C1, C2, done, last_contributor);
                 }
                 warp_done = __all_sync(0xffffffffu, done);
