@@ -26,7 +26,7 @@ class FsFrameInfo(C.Structure):
 _LAYOUT_FIELDS = [
     "total_bytes", "info", "depths", "cov3D", "splat", "clamped", "rect", "tiles_touched", "tile_count",
     "tile_cursor", "ranges", "big_tiles", "work_order", "tile_meta", "seg_base", "seg_info", "ckpt", "final_C", "inst_keys", "inst_keys_alt", "point_list", "inst_splat", "final_T",
-    "n_contrib", "bwd_counter", "grad_acc", "instance_capacity",
+    "n_contrib", "bwd_counter", "grad_acc", "instance_capacity", "pair_mask",
 ]
 
 

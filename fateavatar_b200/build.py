@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 # FATESPLAT_BUILD_OUT: developer knob -- build an experiment variant next to the product library (see FATESPLAT_LIB)
 OUT = os.environ.get("FATESPLAT_BUILD_OUT") or os.path.join(OUT_DIR, "libfatesplat.so")
-SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "blend_forward.cu", "backward.cu", "knn.cu", "pose.cu", "flame.cu", "stats.cu", "exchange.cu", "optim.cu"]
+SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "blend_forward.cu", "backward.cu", "backward_pipe.cu", "knn.cu", "pose.cu", "flame.cu", "stats.cu", "exchange.cu", "optim.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "fatesplat.h")]
 
 NVCC_FLAGS = [

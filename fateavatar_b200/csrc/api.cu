@@ -148,6 +148,7 @@ void fs_compute_layout(int P, int W, int H, size_t Rcap, fs_workspace_layout* L)
     L->n_contrib = take((size_t)W * H * 4);
     L->bwd_counter = take(256 + 1024);  // work counter + 256 per-SM slot counters of the backward blend
     L->grad_acc = take(Pn * 48);
+    L->pair_mask = take(Rcap * 32);
     L->instance_capacity = Rcap;
     L->total_bytes = off;
 }

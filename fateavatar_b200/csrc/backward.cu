@@ -528,6 +528,9 @@ preprocess_backward_kernel(int P, int D, int M, const float* __restrict__ means3
 
 }  // namespace
 
+void fs_launch_blend_backward_pipe(int W, int H, const float* bg, char* ws, const fs_workspace_layout& L,
+                                   const float* dL_dpix, float* grad_acc, cudaStream_t stream);  // backward_pipe.cu
+
 void fs_launch_backward(int P, int D, int M, const float* bg, int W, int H, const float* means3D, const float* shs,
                         const float* colors_precomp, const float* scales, float scale_modifier,
                         const float* rotations, const float* cov3D_precomp, const float* viewmatrix,
@@ -538,7 +541,10 @@ void fs_launch_backward(int P, int D, int M, const float* bg, int W, int H, cons
     float* grad_acc = reinterpret_cast<float*>(ws + L.grad_acc);
     // work counter (256-byte slot) and the per-Gaussian accumulator are contiguous: one memset node
     cudaMemsetAsync(ws + L.bwd_counter, 0, (L.grad_acc - L.bwd_counter) + (size_t)P * 48, stream);
-    {
+    if (fs_tuning("FATESPLAT_BWD_PIPE", 1)) {  // lanes own splats (backward_pipe.cu); 0 = lanes own pixels (below)
+        FsStageTimer timer(FS_STAGE_BLEND_BWD, stream);
+        fs_launch_blend_backward_pipe(W, H, bg, ws, L, dL_dpix, grad_acc, stream);
+    } else {
         FsStageTimer timer(FS_STAGE_BLEND_BWD, stream);
         const size_t smem = sizeof(WarpStage) * kWarps + sizeof(uint64_t) * 2 * kWarps;
         static std::atomic<unsigned long long> attr_set{0};

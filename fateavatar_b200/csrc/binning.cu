@@ -36,6 +36,8 @@ tile_scan_kernel(int Tn, const uint32_t* __restrict__ tile_count, uint32_t* __re
     __shared__ uint32_t s_nbig;
     __shared__ uint32_t s_bin[33];  // tiles per log2(count) class; class 0 = empty
     __shared__ uint32_t s_wseg[32];
+    __shared__ uint32_t s_wfull[32];  // full (FS_SEG-position) segments: they are listed first, partial ones last
+    __shared__ uint32_t s_nfull;
     fs::pdl_trigger();
     fs::pdl_wait();
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -44,22 +46,25 @@ tile_scan_kernel(int Tn, const uint32_t* __restrict__ tile_count, uint32_t* __re
     __syncthreads();
     const int per = (Tn + kScanThreads - 1) / kScanThreads;
     const int beg = min(Tn, tid * per), end = min(Tn, beg + per);
-    uint32_t sum = 0, mx = 0, segs = 0;
+    uint32_t sum = 0, mx = 0, segs = 0, fulls = 0;
     for (int t = beg; t < end; ++t) {
         const uint32_t c = tile_count[(size_t)t * FS_CNT_STRIDE];
         sum += c;
         segs += (c + FS_SEG - 1) / FS_SEG;
+        fulls += c / FS_SEG;
         mx = max(mx, c);
         atomicAdd(&s_bin[c ? 32 - __clz(c) : 0], 1u);
     }
-    uint32_t incl = sum, sincl = segs;
+    uint32_t incl = sum, sincl = segs, fincl = fulls;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
         const uint32_t w = __shfl_up_sync(0xffffffffu, sincl, o);
+        const uint32_t x = __shfl_up_sync(0xffffffffu, fincl, o);
         if (lane >= o) {
             incl += v;
             sincl += w;
+            fincl += x;
         }
     }
 #pragma unroll
@@ -67,6 +72,7 @@ tile_scan_kernel(int Tn, const uint32_t* __restrict__ tile_count, uint32_t* __re
     if (lane == 31) {
         s_warp[wid] = incl;
         s_wseg[wid] = sincl;
+        s_wfull[wid] = fincl;
     }
     if (lane == 0) s_wmax[wid] = mx;
     __syncthreads();
@@ -75,17 +81,23 @@ tile_scan_kernel(int Tn, const uint32_t* __restrict__ tile_count, uint32_t* __re
         uint32_t wi = w;
         uint32_t ws_ = s_wseg[lane];
         uint32_t wsi = ws_;
+        uint32_t wf_ = s_wfull[lane];
+        uint32_t wfi = wf_;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
             const uint32_t v2 = __shfl_up_sync(0xffffffffu, wsi, o);
+            const uint32_t v3 = __shfl_up_sync(0xffffffffu, wfi, o);
             if (lane >= o) {
                 wi += v;
                 wsi += v2;
+                wfi += v3;
             }
         }
         s_warp[lane] = wi - w;  // exclusive prefix of warp totals
         s_wseg[lane] = wsi - ws_;
+        s_wfull[lane] = wfi - wf_;
+        if (lane == 31) s_nfull = wfi;
         if (lane == 31) {
             info->reserved[2] = wsi;  // depth segments in this frame (work units of the backward blend / 8)
             seg_base[Tn] = wsi;
@@ -113,11 +125,19 @@ tile_scan_kernel(int Tn, const uint32_t* __restrict__ tile_count, uint32_t* __re
     __syncthreads();
     uint32_t off = s_warp[wid] + (incl - sum);
     uint32_t soff = s_wseg[wid] + (sincl - segs);
+    // work list of the backward blend: every full segment first (tile order), then the partial ones -- the small
+    // units come last, so the warps run out of work at about the same time
+    uint32_t foff = s_wfull[wid] + (fincl - fulls);
+    uint32_t poff = s_nfull + (soff - foff);
     for (int t = beg; t < end; ++t) {
         const uint32_t c = tile_count[(size_t)t * FS_CNT_STRIDE];
         seg_base[t] = soff;
-        if (off + c <= Rcap)  // an overflowed frame never reads these
-            for (uint32_t k = 0; k < (c + FS_SEG - 1) / FS_SEG; ++k) seg_info[soff + k] = make_uint2((uint32_t)t, k);
+        if (off + c <= Rcap) {  // an overflowed frame never reads these
+            for (uint32_t k = 0; k < c / FS_SEG; ++k) seg_info[foff + k] = make_uint2((uint32_t)t, k);
+            if (c % FS_SEG) seg_info[poff] = make_uint2((uint32_t)t, c / FS_SEG);
+        }
+        foff += c / FS_SEG;
+        poff += (c % FS_SEG) ? 1u : 0u;
         soff += (c + FS_SEG - 1) / FS_SEG;
         tile_cursor[(size_t)t * FS_CNT_STRIDE] = off;
         ranges[t] = c ? make_uint2(off, off + c) : make_uint2(0u, 0u);  // empty tiles stay (0,0) like the memset

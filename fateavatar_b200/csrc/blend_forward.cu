@@ -72,8 +72,9 @@ __device__ __forceinline__ void compute_group(Group& g, unsigned& m, int c, cons
 }
 
 // sequential transmittance update (front-to-back order), fully predicated
-__device__ __forceinline__ void apply_group(const Group& g, uint32_t base, float& T, float& C0, float& C1, float& C2,
-                                            bool& done, uint32_t& last_contributor) {
+__device__ __forceinline__ void apply_group(const Group& g, uint32_t base, int c, int lane, float& T, float& C0,
+                                            float& C1, float& C2, bool& done, uint32_t& last_contributor,
+                                            uint32_t& my_mask) {
 #pragma unroll
     for (int k = 0; k < kGroup; ++k) {
         const float test_T = fs::mul(T, fs::sub(1.0f, g.alpha[k]));
@@ -89,6 +90,10 @@ __device__ __forceinline__ void apply_group(const Group& g, uint32_t base, float
         C2 = apply ? n2 : C2;
         T = apply ? test_T : T;
         last_contributor = apply ? base + (uint32_t)g.jj[k] + 1u : last_contributor;
+        // which pixels of the block blended this record: kept by the lane that tested the record, stored once per
+        // 32 records (pair_mask; the backward blend reads the decisions instead of re-deriving them)
+        const unsigned bm = __ballot_sync(0xffffffffu, apply);
+        my_mask |= (lane == g.jj[k] - c) ? bm : 0u;
     }
 }
 
@@ -98,7 +103,7 @@ blend_forward_kernel(const uint4* __restrict__ tile_meta, const uint32_t* __rest
                      uint32_t* __restrict__ sm_slots, uint32_t* __restrict__ work_counter, const SplatRec* __restrict__ inst_splat, int W, int H,
                      float4* __restrict__ ckpt, float4* __restrict__ final_C,
                      const float* __restrict__ bg_color, float* __restrict__ out_color, float* __restrict__ final_T,
-                     uint32_t* __restrict__ n_contrib, uint32_t Rcap) {
+                     uint32_t* __restrict__ n_contrib, uint32_t* __restrict__ pair_mask, uint32_t Rcap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     WarpStage* stages = reinterpret_cast<WarpStage*>(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sizeof(WarpStage) * kWarps);
@@ -171,6 +176,7 @@ blend_forward_kernel(const uint4* __restrict__ tile_meta, const uint32_t* __rest
         // checkpoints for the backward blend: per-pixel (T, C) before list positions k*FS_SEG, k = 1, 2, ...
         float4* ck = ckpt + (size_t)meta.z * FS_TILE_PIX + ((by - tile_y * FS_TILE) + (lane >> 3)) * FS_TILE +
                      (bx - tile_x * FS_TILE) + (lane & 7);
+        uint32_t* mask_out = pair_mask + (size_t)range.x * 8u + (size_t)blk * total;
 
         int b = 0;
         for (; b < nbatches; ++b) {
@@ -192,6 +198,7 @@ blend_forward_kernel(const uint4* __restrict__ tile_meta, const uint32_t* __rest
                           !(q0.x + q0.z < wx0 || q0.x - q0.z > wx1 || q0.y + q0.w < wy0 || q0.y - q0.w > wy1);
                 }
                 unsigned m = __ballot_sync(0xffffffffu, hit);
+                uint32_t my_mask = 0u;
                 // Survivors are walked four at a time.  The vote ends the basic block, so all four alphas are
                 // needed at once and the scheduler overlaps the four power/exp chains instead of trailing them
                 // behind the (short, sequential) transmittance chain; it also skips groups that touch no pixel.
@@ -202,8 +209,9 @@ blend_forward_kernel(const uint4* __restrict__ tile_meta, const uint32_t* __rest
 #pragma unroll
                     for (int k = 0; k < kGroup; ++k) any_a |= g.alpha[k] >= 0.0f;
                     if (!__any_sync(0xffffffffu, any_a)) continue;
-                    apply_group(g, (uint32_t)b * kBatch, T, C0, C1, C2, done, last_contributor);
+                    apply_group(g, (uint32_t)b * kBatch, c, lane, T, C0, C1, C2, done, last_contributor, my_mask);
                 }
+                if (j < cnt) mask_out[(size_t)b * kBatch + j] = my_mask;
                 warp_done = __all_sync(0xffffffffu, done);
             }
             if (warp_done) {  // every pixel of the block has terminated: stop streaming
@@ -251,6 +259,6 @@ void fs_launch_blend_forward(int W, int H, const float* bg, float* out_color, ch
         reinterpret_cast<float4*>(ws + L.ckpt),
         reinterpret_cast<float4*>(ws + L.final_C), bg, out_color,
         reinterpret_cast<float*>(ws + L.final_T), reinterpret_cast<uint32_t*>(ws + L.n_contrib),
-        (uint32_t)L.instance_capacity);
+        reinterpret_cast<uint32_t*>(ws + L.pair_mask), (uint32_t)L.instance_capacity);
     fs_count_launch(1);
 }

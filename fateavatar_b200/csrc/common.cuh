@@ -7,7 +7,9 @@
 
 #define FS_TILE 16
 #define FS_TILE_PIX 256
+#ifndef FS_SEG
 #define FS_SEG 256  // list positions per depth segment (unit of backward-blend parallelism along a tile's list)
+#endif
 
 // Splat record: 3 x float4 per Gaussian.
 //   q0 = {mean2D.x, mean2D.y, extent.x, extent.y}   extent = conservative half-size of the region where

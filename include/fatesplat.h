@@ -86,6 +86,10 @@ typedef struct fs_workspace_layout {
     size_t bwd_counter;   /* uint32 (256-byte slot) work counter of the backward blend, directly before grad_acc */
     size_t grad_acc;      /* float  [P][12]  backward accumulator: dmean2D.xy, dconic.xyw, dopacity, drgb, 3 pad */
     size_t instance_capacity; /* Rcap (count, not bytes)                                     */
+    size_t pair_mask;     /* uint32 [Rcap][8] written by the forward blend: for tile t (list range [s,e)), 8x4 block b
+                             and list position j the word at (8*s + b*(e-s) + j) has bit p set iff pixel p of the
+                             block blended that instance -- the backward blend reads the forward's decisions
+                             instead of re-deriving them */
 } fs_workspace_layout;
 
 /* Size/layout of the workspace for P Gaussians, a W x H image and room for `instance_capacity` instances. */
