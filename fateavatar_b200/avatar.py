@@ -118,6 +118,18 @@ def quaternion_to_axis_angle(q):
     return q[..., 1:] / s
 
 
+_zeros = {}
+
+
+def _cached_zeros(shape, device, dtype):
+    """Read-only zeros, one allocation per (shape, device, dtype)."""
+    key = (shape, str(device), dtype)
+    z = _zeros.get(key)
+    if z is None:
+        z = _zeros[key] = torch.zeros(shape, device=device, dtype=dtype)
+    return z
+
+
 def forward_frame(model, input, exact_camera=None, extras=True):
     """`exact_camera` (default: `model.exact_camera` if set, else False) selects FrameCamera(exact=True).
     `extras=False` leaves out the two outputs that only the scale / rotation regularisers read ("scale" = exp(_scaling),
@@ -142,7 +154,7 @@ def forward_frame(model, input, exact_camera=None, extras=True):
         fm = model._fs_flame_model = _flame.model_tensors(model.flame)
     n_shape, n_exp = int(model.flame.n_shape), int(model.flame.n_exp)
     e = expression[:, :n_exp]
-    betas = torch.cat([torch.zeros(1, n_shape, device=e.device, dtype=e.dtype), e], dim=1)  # flame/FLAME.py:180
+    betas = torch.cat([_cached_zeros((1, n_shape), e.device, e.dtype), e], dim=1)  # flame/FLAME.py:180
     verts, _, _, verts_orig, _ = _flame.flame_lbs(
         fm, betas, flame_pose,
         model.delta_shapedirs if cfg.delta_blendshape else None, model.delta_posedirs if cfg.delta_blendshape else None,
@@ -151,7 +163,9 @@ def forward_frame(model, input, exact_camera=None, extras=True):
                                                 model.face_scaling_canonical, model._scaling, model._rotation,
                                                 model._offset, model._opacity, shell_len=model.shell_len,
                                                 resize_scale=bool(cfg.resize_scale))
-    screenspace = torch.zeros_like(xyz, requires_grad=True)  # render_3dgs.py:22-27: .grad feeds the densifier
+    # render_3dgs.py:22-27: a zero tensor whose .grad feeds the densifier.  No kernel reads or writes its values, so
+    # every frame gets a fresh leaf over one shared block of zeros instead of a fill kernel
+    screenspace = _cached_zeros(tuple(xyz.shape), xyz.device, xyz.dtype).detach().requires_grad_(True)
     settings = _rasterizer.GaussianRasterizationSettings(
         image_height=camera.image_height, image_width=camera.image_width, tanfovx=math.tan(camera.FoVx * 0.5),
         tanfovy=math.tan(camera.FoVy * 0.5), bg=model.bg_color.to(xyz.device), scale_modifier=1.0,

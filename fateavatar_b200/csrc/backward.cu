@@ -320,6 +320,7 @@ preprocess_backward_kernel(int P, int D, int M, const float* __restrict__ means3
                            float* __restrict__ dL_dcolors, float* __restrict__ dL_dmeans3D,
                            float* __restrict__ dL_dcov3D, float* __restrict__ dL_dsh, float* __restrict__ dL_dscales,
                            float* __restrict__ dL_drots) {
+    fs::pdl_trigger();  // a PDL-launched successor (fs_densify_stats_inc) may begin launching; it waits for this grid
     fs::pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;

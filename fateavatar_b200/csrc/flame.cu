@@ -123,7 +123,9 @@ flame_blend_kernel(int V, int L, int l0, int J, const float* __restrict__ betas,
     const bool vec = ((L | l0) & 3) == 0;  // rows start 16-byte aligned and hold whole float4s
     const int nslot = 2 * J * 3;
     float jp0 = 0.f, jp1 = 0.f;  // joint partial sums of slots lane, lane + 32
-    fs::pdl_trigger();  // the skin kernel may start its own prologue (rotations, pose correctives) right away
+    fs::pdl_wait();     // launched while the previous frame's last kernel (or the optimiser step) drains
+    fs::pdl_trigger();  // the skin kernel may start its own prologue (rotations, pose correctives) right away; only
+                        // after the wait, so that nothing it reads early can still be in flight
 
     for (int v = blockIdx.x * (kBlendThreads / 32) + wid; v < V; v += nw) {
         float jw[2];  // this lane's joint-regressor weights, requested together with the blendshape rows
@@ -230,6 +232,7 @@ flame_skin_kernel(int V, int J, Parents parents, int nblk_blend, const float* __
     __shared__ float s_vp[2][kSkinCoords], s_po[2][kSkinCoords], s_pd[2][kSkinCoords];
     const int t = threadIdx.x;
     const int NP = (J - 1) * 9, n3 = 3 * V;
+    fs::pdl_trigger();  // a PDL-launched successor (fs_pose_forward) may begin launching; it waits for this grid
     // ---- everything that does not depend on the blend kernel runs before the wait and overlaps it -------------
     if (t >= 192 && t < 192 + J) {
         const int j = t - 192;
@@ -355,6 +358,7 @@ flame_skin_backward_kernel(int V, int J, const float* __restrict__ lbs_weights, 
     const int t = threadIdx.x;
     const int v0 = blockIdx.x * kSkinVerts;
     const int e = blockIdx.x * kSkinBwdThreads + t, n3 = 3 * V;
+    fs::pdl_wait();  // launched while the producer of dL/dverts (fs_pose_backward) drains
     for (int i = t; i < J * 12; i += kSkinBwdThreads) s_A[i / 12][i % 12] = state->A[0][i / 12][i % 12];
     s_g[t] = e < n3 ? dL_dverts[e] : 0.0f;
     s_vp[t] = e < n3 ? v_posed[e] : 0.0f;
@@ -445,6 +449,7 @@ flame_blend_backward_kernel(int V, int L, int l0, int J, Parents parents, int nb
     __shared__ FlameState S;  // forward state (joints, rotations, chain): one round trip instead of one per use
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const int NP = (J - 1) * 9, n3 = 3 * V;
+    fs::pdl_trigger();  // the next frame's first kernel may begin launching; it waits for this grid
     for (int i = t; i < (int)(sizeof(FlameState) / sizeof(float)); i += kBlendBwdThreads)
         reinterpret_cast<float*>(&S)[i] = reinterpret_cast<const float*>(state)[i];  // written by the forward call
     fs::pdl_wait();
@@ -781,7 +786,7 @@ int fs_flame_forward(int V, int L, int l0, int J, const int* parents_host, const
     char* ws = static_cast<char*>(d_workspace);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     FsStageTimer timer(FS_STAGE_FLAME_FWD, st);
-    flame_blend_kernel<<<w.nblk_blend, kBlendThreads, 0, st>>>(
+    fs_launch_pdl(flame_blend_kernel, dim3(w.nblk_blend), dim3(kBlendThreads), 0, st,
         V, L, l0, J, d_betas, d_v_template, d_delta_vertex, d_shapedirs, d_delta_shapedirs, d_J_regressor,
         reinterpret_cast<float*>(ws + w.v_shaped), reinterpret_cast<float*>(ws + w.jpart));
     fs_launch_pdl(flame_skin_kernel, dim3(w.nblk_skin), dim3(kSkinThreads), 0, st, V, J, P, w.nblk_blend, d_pose,
@@ -825,7 +830,7 @@ int fs_flame_backward(int V, int L, int l0, int J, const int* parents_host, cons
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     FsStageTimer timer(FS_STAGE_FLAME_BWD, st);
     float* g_posed = reinterpret_cast<float*>(ws + w.g_posed);  // kept for fs_flame_backward_coeffs
-    flame_skin_backward_kernel<<<w.nblk_skin, kSkinBwdThreads, 0, st>>>(
+    fs_launch_pdl(flame_skin_backward_kernel, dim3(w.nblk_skin), dim3(kSkinBwdThreads), 0, st,
         V, J, d_lbs_weights, reinterpret_cast<const FlameState*>(ws + w.state),
         reinterpret_cast<const float*>(ws + w.v_posed), d_dL_dverts, g_posed, d_dL_dv_posed,
         reinterpret_cast<float*>(ws + w.dapart));

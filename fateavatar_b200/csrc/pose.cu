@@ -105,6 +105,7 @@ pose_forward_kernel(int N, const float* __restrict__ verts, const long long* __r
                     const float* __restrict__ opacity_raw, float shell_len, int resize_scale,
                     float* __restrict__ means3D, float* __restrict__ scales, float* __restrict__ rotations,
                     float* __restrict__ opacities) {
+    fs::pdl_wait();  // launched while the FLAME skin kernel drains (fs_launch_pdl)
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     const long long f = face_index[n];
@@ -141,6 +142,23 @@ __device__ __forceinline__ V3 normalize_bwd(V3 u, float len, float dot_xx, V3 du
     return (du - u * dot(u, du)) * (1.0f / len);
 }
 
+// dL/dverts[i] += v: rows are 12 bytes apart, so an even row starts 8-byte aligned (x,y as one red.v2 + z) and an odd
+// row ends 8-byte aligned (x + y,z as one red.v2): two reductions per vertex instead of three
+__device__ __forceinline__ void red_add3(float* __restrict__ base, long long i, V3 v) {
+    float* p = base + 3 * i;
+    if ((i & 1) == 0 && (reinterpret_cast<uintptr_t>(base) & 7u) == 0) {
+        asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+        atomicAdd(p + 2, v.z);
+    } else if ((reinterpret_cast<uintptr_t>(base) & 7u) == 0) {
+        atomicAdd(p, v.x);
+        asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p + 1), "f"(v.y), "f"(v.z) : "memory");
+    } else {
+        atomicAdd(p, v.x);
+        atomicAdd(p + 1, v.y);
+        atomicAdd(p + 2, v.z);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 pose_backward_kernel(int N, const float* __restrict__ verts, const long long* __restrict__ faces,
                      const long long* __restrict__ face_index, const float* __restrict__ bary,
@@ -151,6 +169,7 @@ pose_backward_kernel(int N, const float* __restrict__ verts, const long long* __
                      const float* __restrict__ g_rotations, const float* __restrict__ g_opacities,
                      float* __restrict__ d_verts, float* __restrict__ d_scaling_raw, float* __restrict__ d_rotation_raw,
                      float* __restrict__ d_offset_raw, float* __restrict__ d_opacity_raw) {
+    fs::pdl_trigger();  // the FLAME skin backward may begin launching; it waits for this grid before reading
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     const long long f = face_index[n];
@@ -263,9 +282,9 @@ pose_backward_kernel(int N, const float* __restrict__ verts, const long long* __
     // vertices
     const V3 d_v0 = g * b0 - d_e1 - d_e2, d_v1 = g * b1 + d_e1, d_v2 = g * b2 + d_e2;
     const long long i0 = faces[3 * f], i1 = faces[3 * f + 1], i2 = faces[3 * f + 2];
-    atomicAdd(d_verts + 3 * i0, d_v0.x); atomicAdd(d_verts + 3 * i0 + 1, d_v0.y); atomicAdd(d_verts + 3 * i0 + 2, d_v0.z);
-    atomicAdd(d_verts + 3 * i1, d_v1.x); atomicAdd(d_verts + 3 * i1 + 1, d_v1.y); atomicAdd(d_verts + 3 * i1 + 2, d_v1.z);
-    atomicAdd(d_verts + 3 * i2, d_v2.x); atomicAdd(d_verts + 3 * i2 + 1, d_v2.y); atomicAdd(d_verts + 3 * i2 + 2, d_v2.z);
+    red_add3(d_verts, i0, d_v0);
+    red_add3(d_verts, i1, d_v1);
+    red_add3(d_verts, i2, d_v2);
 }
 
 }  // namespace
@@ -288,7 +307,7 @@ int fs_pose_forward(int N, int V, int F, const float* d_verts, const long long* 
         return FS_ERR_INVALID_ARGUMENT;
     }
     FsStageTimer timer(FS_STAGE_POSE_FWD, static_cast<cudaStream_t>(stream));
-    pose_forward_kernel<<<(N + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    fs_launch_pdl(pose_forward_kernel, dim3((N + 255) / 256), dim3(256), 0, static_cast<cudaStream_t>(stream),
         N, d_verts, d_faces, d_face_index, d_bary, d_face_scale_canonical, d_scaling_raw, d_rotation_raw, d_offset_raw,
         d_opacity_raw, shell_len, resize_scale, d_means3D, d_scales, d_rotations, d_opacities);
     fs_count_launch(1);

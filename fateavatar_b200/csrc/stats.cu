@@ -21,6 +21,7 @@ densify_stats_kernel(int P, const float* __restrict__ grad2d /*[P,3]*/, const ui
 __global__ void __launch_bounds__(256)
 densify_stats_inc_kernel(int P, const float* __restrict__ grad2d, const int* __restrict__ radii,
                          float* __restrict__ accum_inc, float* __restrict__ denom_inc) {
+    fs::pdl_wait();  // launched while the per-Gaussian backward drains (fs_launch_pdl)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     const bool vis = radii[i] > 0;
@@ -87,28 +88,50 @@ l1_loss_kernel(size_t n, const float* __restrict__ x, const float* __restrict__ 
     __shared__ bool s_last;
     const float inv_n = 1.0f / (float)n;
     float acc = 0.0f;
-    for (size_t i = (size_t)blockIdx.x * kL1Threads + threadIdx.x; i < n; i += (size_t)gridDim.x * kL1Threads) {
+    const size_t stride = (size_t)gridDim.x * kL1Threads;
+    const size_t n4 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(t) | reinterpret_cast<uintptr_t>(grad)) & 15u) ? 0 : n / 4;
+    for (size_t i = (size_t)blockIdx.x * kL1Threads + threadIdx.x; i < n4; i += stride) {  // 128-bit body
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x) + i), b = __ldg(reinterpret_cast<const float4*>(t) + i);
+        const float d0 = a.x - b.x, d1 = a.y - b.y, d2 = a.z - b.z, d3 = a.w - b.w;
+        acc += (fabsf(d0) + fabsf(d1)) + (fabsf(d2) + fabsf(d3));
+        reinterpret_cast<float4*>(grad)[i] =
+            make_float4(d0 > 0.0f ? inv_n : (d0 < 0.0f ? -inv_n : 0.0f), d1 > 0.0f ? inv_n : (d1 < 0.0f ? -inv_n : 0.0f),
+                        d2 > 0.0f ? inv_n : (d2 < 0.0f ? -inv_n : 0.0f), d3 > 0.0f ? inv_n : (d3 < 0.0f ? -inv_n : 0.0f));
+    }
+    for (size_t i = n4 * 4 + (size_t)blockIdx.x * kL1Threads + threadIdx.x; i < n; i += stride) {  // tail / unaligned
         const float d = x[i] - t[i];
         acc += fabsf(d);
         grad[i] = d > 0.0f ? inv_n : (d < 0.0f ? -inv_n : 0.0f);
     }
+    // fixed-shape tree inside the CTA, per-CTA partials, and the last CTA to finish adds the partials with the same
+    // fixed-shape tree: the result does not depend on which CTA finishes last
+    auto block_sum = [&](float v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+        __syncthreads();
         float b = 0.0f;
-        for (int w = 0; w < kL1Threads / 32; ++w) b += s_w[w];
-        partial[blockIdx.x] = b;
+        if (threadIdx.x == 0)
+            for (int w = 0; w < kL1Threads / 32; ++w) b += s_w[w];
+        return b;  // valid in thread 0
+    };
+    const float mine = block_sum(acc);
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = mine;
         __threadfence();
         s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (s_last && threadIdx.x == 0) {
-        float total = 0.0f;
-        for (unsigned int b = 0; b < gridDim.x; ++b) total += *reinterpret_cast<volatile float*>(partial + b);
-        *loss = total * inv_n;
-        *counter = 0u;
+    if (s_last) {
+        __threadfence();
+        float v = 0.0f;
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += kL1Threads) v += *reinterpret_cast<volatile float*>(partial + b);
+        const float total = block_sum(v);
+        if (threadIdx.x == 0) {
+            *loss = total * inv_n;
+            *counter = 0u;
+        }
     }
 }
 
@@ -144,7 +167,7 @@ extern "C" int fs_densify_stats_inc(int P, const float* d_viewspace_grad, const 
         fs_set_error("fs_densify_stats_inc: required pointer is NULL");
         return FS_ERR_INVALID_ARGUMENT;
     }
-    densify_stats_inc_kernel<<<(P + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    fs_launch_pdl(densify_stats_inc_kernel, dim3((P + 255) / 256), dim3(256), 0, static_cast<cudaStream_t>(stream),
         P, d_viewspace_grad, d_radii, d_accum_inc, d_denom_inc);
     fs_count_launch(1);
     if (cudaGetLastError() != cudaSuccess) {
