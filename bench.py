@@ -726,6 +726,18 @@ def main():
                 "algorithmic_bytes": alg[dom], "kernel_us": stage_us.get(dom),
                 "note": "the blend kernels are issue/SFU bound (about 1 exp + 60-130 instructions per pixel-splat "
                         "pair on a few MB of records), so the HBM fraction is low by construction; see DESIGN.md"}
+    try:  # the blend kernels' own work counters (frame 0 of the ring, last eager step): evaluated exp and blended pairs
+        wf, wb = taps["work_forward"].cpu().tolist(), taps["work_backward"].cpu().tolist()
+        roofline["device_work"] = {
+            "forward_block_instance_pairs": wf[0], "forward_exp_evaluated": 32 * wf[0],
+            "backward_block_instance_pairs": wb[0], "backward_exp_evaluated": 32 * wb[0], "blended_pairs": wb[1],
+            "forward_exp_per_s": 32 * wf[0] / (stage_us["blend_forward"] * 1e-6) if stage_us.get("blend_forward") else None,
+            "backward_exp_per_s": 32 * wb[0] / (stage_us["blend_backward"] * 1e-6) if stage_us.get("blend_backward") else None,
+            "note": "counted on the device by the blend kernels themselves (fs_workspace_layout: info + 1056, "
+                    "bwd_counter + 16): every (8x4 block, instance) pair a kernel takes in costs 32 exp evaluations; "
+                    "blended_pairs = (pixel, instance) pairs with a colour / gradient contribution"}
+    except Exception as ex:
+        roofline["device_work"] = {"error": repr(ex)}
     kernels = {k: {"us": round(v, 2), "alg_bytes": alg.get(k),
                    "gbs": round(alg[k] / (v * 1e-6) / 1e9, 1) if k in alg else None} for k, v in stage_us.items()}
 

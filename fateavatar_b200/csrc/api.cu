@@ -122,7 +122,8 @@ void fs_compute_layout(int P, int W, int H, size_t Rcap, fs_workspace_layout* L)
         return o;
     };
     memset(L, 0, sizeof(*L));
-    L->info = take(sizeof(fs_frame_info) + 1024);  // header + 256 per-SM slot counters of the forward blend
+    // header + 256 per-SM slot counters of the forward blend + 16 work counters (FS_WORK_*, common.cuh)
+    L->info = take(sizeof(fs_frame_info) + 1024 + 64);
     L->tile_count = take(Tn * 4 * FS_CNT_STRIDE);  // directly after the header: one memset clears both
     L->tile_cursor = take(Tn * 4 * FS_CNT_STRIDE);
     L->ranges = take(Tn * 8);

@@ -255,6 +255,7 @@ blend_backward_pipe_kernel(const uint4* __restrict__ tile_meta, const uint2* __r
     bool all_pulled = false, drained = false;
     uint32_t pending_unit = 0;         // a unit that was pulled but had to wait for a pixel table
     bool have_pending = false;
+    uint32_t n_splats = 0, n_pairs = 0;  // work counters: splats taken in (uniform), blended pairs (per lane)
 
     auto issue = [&](int k) {  // lane 0 only: TMA of chunk k of the current unit into the ring
         const uint32_t lo = seg_lo + (uint32_t)k * kChunk;
@@ -352,7 +353,9 @@ blend_backward_pipe_kernel(const uint4* __restrict__ tile_meta, const uint2* __r
             const SplatRec* rec = ws->ring[fills & 1u];
             ++fills;
             ++kb;
+            n_pairs += (uint32_t)__popc(mk);
             if (m != 0u) {
+                n_splats += (uint32_t)__popc(m);
                 if (mk != 0u) {
                     const uint32_t rank = (uint32_t)__popc(m & lt_mask);
                     uint32_t slot = head + pend + rank;
@@ -395,6 +398,13 @@ blend_backward_pipe_kernel(const uint4* __restrict__ tile_meta, const uint2* __r
             ++windows;
             pend = pend >= 32u ? pend - 32u : 0u;
         }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_pairs += __shfl_xor_sync(0xffffffffu, n_pairs, o);
+    if (lane == 0 && n_splats) {
+        uint32_t* stats = work_counter + FS_WORK_BWD_OFFSET / 4;
+        atomicAdd(stats + FS_WORK_BWD_SPLATS, n_splats);
+        atomicAdd(stats + FS_WORK_BWD_PAIRS, n_pairs);
     }
 }
 

@@ -43,6 +43,35 @@ struct Group {
     bool any;
 };
 
+// Second, exact stage of the cull (the first is the bounding box of the alpha >= 1/255 ellipse): the largest alpha the
+// splat reaches anywhere on the block's rectangle.  alpha >= 1/255 needs q(d) = 1/2 (A dx^2 + C dy^2) + B dx dy <=
+// tau = ln(255 o), d = mean - pixel.  q is convex, so its minimum over the rectangle is 0 when the mean lies inside and
+// otherwise sits on the edge(s) facing the mean: on the edge dx = X the minimiser is dy = clamp(-B X / C), and the
+// interior of an edge that does not face the mean can never hold the minimum (there dq/dx = X det / C points inward).
+// Continuous minimum <= minimum over the block's pixels, and 0.01 covers the fp32 rounding of both sides, so a record
+// rejected here could not have been blended by any pixel of the block; positions in the list are still counted.
+__device__ __forceinline__ bool ellipse_reaches_block(float mx, float my, float4 con_o, float wx0, float wx1, float wy0,
+                                                      float wy1) {
+    const float A = con_o.x, B = con_o.y, C = con_o.z;
+    if (!(A > 0.0f && C > 0.0f && A * C - B * B > 0.0f)) return true;  // not an ellipse: leave it to the blend rule
+    const float X0 = mx - wx1, X1 = mx - wx0, Y0 = my - wy1, Y1 = my - wy0;  // d ranges over [X0,X1] x [Y0,Y1]
+    const bool xin = X0 <= 0.0f && X1 >= 0.0f, yin = Y0 <= 0.0f && Y1 >= 0.0f;
+    if (xin && yin) return true;
+    float qmin = 3.0e38f;
+    if (!xin) {
+        const float X = X0 > 0.0f ? X0 : X1;
+        const float y = fminf(fmaxf(__fdividef(-B * X, C), Y0), Y1);
+        qmin = 0.5f * (A * X * X + C * y * y) + B * X * y;
+    }
+    if (!yin) {
+        const float Y = Y0 > 0.0f ? Y0 : Y1;
+        const float x = fminf(fmaxf(__fdividef(-B * Y, A), X0), X1);
+        qmin = fminf(qmin, 0.5f * (A * x * x + C * Y * Y) + B * x * Y);
+    }
+    const float tau = __logf(255.0f * con_o.w);
+    return !(qmin > tau + 0.01f);
+}
+
 // extract the next (up to) four set bits of m and evaluate alpha for this lane's pixel
 __device__ __forceinline__ void compute_group(Group& g, unsigned& m, int c, const SplatRec* __restrict__ rec, float pxf,
                                               float pyf) {
@@ -103,7 +132,8 @@ blend_forward_kernel(const uint4* __restrict__ tile_meta, const uint32_t* __rest
                      uint32_t* __restrict__ sm_slots, uint32_t* __restrict__ work_counter, const SplatRec* __restrict__ inst_splat, int W, int H,
                      float4* __restrict__ ckpt, float4* __restrict__ final_C,
                      const float* __restrict__ bg_color, float* __restrict__ out_color, float* __restrict__ final_T,
-                     uint32_t* __restrict__ n_contrib, uint32_t* __restrict__ pair_mask, uint32_t Rcap) {
+                     uint32_t* __restrict__ n_contrib, uint32_t* __restrict__ pair_mask,
+                     uint32_t* __restrict__ work_stats, uint32_t Rcap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     WarpStage* stages = reinterpret_cast<WarpStage*>(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sizeof(WarpStage) * kWarps);
@@ -135,6 +165,7 @@ blend_forward_kernel(const uint4* __restrict__ tile_meta, const uint32_t* __rest
     }
     __syncwarp();
     uint32_t fills = 0;  // batches issued so far by this warp: stage = fills & 1, parity = (fills >> 1) & 1
+    uint32_t n_box = 0;  // records that passed the box cull (warp-uniform)
 
     const int gx = (W + FS_TILE - 1) / FS_TILE;
     const float bg0 = __ldg(bg_color + 0), bg1 = __ldg(bg_color + 1), bg2 = __ldg(bg_color + 2);
@@ -196,8 +227,10 @@ blend_forward_kernel(const uint4* __restrict__ tile_meta, const uint32_t* __rest
                     const float4 q0 = rec[j].q0;
                     hit = !(q0.z < 0.0f) &&
                           !(q0.x + q0.z < wx0 || q0.x - q0.z > wx1 || q0.y + q0.w < wy0 || q0.y - q0.w > wy1);
+                    if (hit) hit = ellipse_reaches_block(q0.x, q0.y, rec[j].q1, wx0, wx1, wy0, wy1);
                 }
                 unsigned m = __ballot_sync(0xffffffffu, hit);
+                n_box += (uint32_t)__popc(m);
                 uint32_t my_mask = 0u;
                 // Survivors are walked four at a time.  The vote ends the basic block, so all four alphas are
                 // needed at once and the scheduler overlaps the four power/exp chains instead of trailing them
@@ -238,6 +271,7 @@ blend_forward_kernel(const uint4* __restrict__ tile_meta, const uint32_t* __rest
             out_color[2 * plane + pid] = fs::mad(bg2, T, C2);
         }
     }
+    if (lane == 0 && n_box) atomicAdd(work_stats + FS_WORK_FWD_BOX, n_box);
 }
 
 }  // namespace
@@ -259,6 +293,7 @@ void fs_launch_blend_forward(int W, int H, const float* bg, float* out_color, ch
         reinterpret_cast<float4*>(ws + L.ckpt),
         reinterpret_cast<float4*>(ws + L.final_C), bg, out_color,
         reinterpret_cast<float*>(ws + L.final_T), reinterpret_cast<uint32_t*>(ws + L.n_contrib),
-        reinterpret_cast<uint32_t*>(ws + L.pair_mask), (uint32_t)L.instance_capacity);
+        reinterpret_cast<uint32_t*>(ws + L.pair_mask), reinterpret_cast<uint32_t*>(ws + L.info + FS_WORK_FWD_OFFSET),
+        (uint32_t)L.instance_capacity);
     fs_count_launch(1);
 }

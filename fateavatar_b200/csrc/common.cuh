@@ -217,6 +217,14 @@ inline cudaError_t fs_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Work counters of the blend kernels: uint32 words at workspace offset info + sizeof(fs_frame_info) + 1024 (forward,
+// cleared with the header) and at bwd_counter + 16 bytes (backward, cleared with the backward's work counter).
+#define FS_WORK_FWD_OFFSET (sizeof(fs_frame_info) + 1024)
+#define FS_WORK_FWD_BOX 0    // (block, instance) pairs that passed the forward's box cull: each costs 32 exp evaluations
+#define FS_WORK_BWD_OFFSET 16
+#define FS_WORK_BWD_SPLATS 0 // (block, instance) pairs the backward pipeline took in (non-zero pair mask): 32 exp each
+#define FS_WORK_BWD_PAIRS 1  // (pixel, instance) pairs that were blended == pairs with a gradient contribution
+
 #ifndef FS_SORT_SMEM_CAP
 #define FS_SORT_SMEM_CAP 4096  // instances a tile may hold to be sorted by the one-CTA-per-tile kernel
 #endif

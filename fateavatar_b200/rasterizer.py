@@ -491,5 +491,9 @@ def decode_workspace(workspace, P, W, H, capacity, num_rendered=None):
         inst_splat=view(L.inst_splat, R * 48, torch.float32, (R, 12)),
         final_T=view(L.final_T, W * H * 4, torch.float32, (H, W)),
         n_contrib=view(L.n_contrib, W * H * 4, torch.int32, (H, W)),
+        # work counters of the blend kernels (common.cuh FS_WORK_*): [0] (block, instance) pairs behind the forward's
+        # box cull; after a backward: [0] (block, instance) pairs it took in, [1] blended (pixel, instance) pairs
+        work_forward=view(L.info + 32 + 1024, 64, torch.int32, (16,)),
+        work_backward=view(L.bwd_counter + 16, 8, torch.int32, (2,)),
     )
     return out

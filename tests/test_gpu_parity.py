@@ -86,6 +86,13 @@ def test_forward_backward_vs_oracle(name, cuda_device):
     og = orc.backward(o, dpix)
     for k in GRAD_NAMES:
         assert_grad_close(k, grads[k].cpu().numpy(), og[k])
+    # the blend kernels' own work counters: the pairs the backward pipeline blended are the pairs the reference's
+    # forward blends (a threshold-fragile pixel may gain or lose one), taken in through at most as many
+    # (block, instance) pairs as the forward's box cull let pass
+    pc = orc.pair_counts(o)
+    wf, wb = taps["work_forward"].cpu().numpy(), taps["work_backward"].cpu().numpy()
+    assert abs(int(wb[1]) - pc["contributing"]) <= 2 * int(o["fragile"].sum()) + 2, (wb, pc)
+    assert 0 <= int(wb[0]) <= int(wf[0]) and 32 * int(wb[0]) >= int(wb[1])
 
 
 def test_very_large_tile_list_global_sort_path(cuda_device):

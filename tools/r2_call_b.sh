@@ -1,0 +1,7 @@
+#!/bin/bash
+# N=1: parity suite, ncu launch list + full captures (profiles), full bench line under the driver's arguments
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+bash tools/make_profiles.sh r02 > gpurun_out/r02_make_profiles.log 2>&1
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err; echo "bench rc=$?"; tail -c 400 gpurun_out/r02_bench_n1.err
+timeout 300 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r02_bench_ref.json 2> gpurun_out/r02_bench_ref.err; echo "ref rc=$?"

@@ -47,7 +47,7 @@ def to_bytes(v, unit):
     return v * m.get(unit, 1)
 dram = {}
 for r in rr[2:]:
-    name = short(r[idx["Kernel Name"]]).replace("_kernel", "")
+    name = short(r[idx["Kernel Name"]]).replace("_kernel", "").replace("blend_backward_pipe", "blend_backward")
     b = to_bytes(num(r[idx["dram__bytes_read.sum"]]), u[idx["dram__bytes_read.sum"]]) + to_bytes(num(r[idx["dram__bytes_write.sum"]]), u[idx["dram__bytes_write.sum"]])
     dram[name] = b
 summary = {"round": R, "command": "python bench.py --quick --steps 4 --warmup 3 (config 2: 512x512, 100k Gaussians)",
