@@ -64,8 +64,10 @@ def parse():
 
 
 def workload_config(args):
-    return {"workload": f"config2: FateAvatar-scale FLAME-posed head mesh, {args.P} Gaussians, {args.res}x{args.res}, SH0, "
-                        f"FLAME lbs + pose + render forward + backward (to splat parameters and FLAME deltas) per frame",
+    return {"workload": f"config2: FateAvatar-scale FLAME-posed head mesh (synthetic head-sized ellipsoid, V=5002 / F=10000 "
+                        f"with a FLAME-shaped model; the licensed template has 5023 / 10006), {args.P} Gaussians, "
+                        f"{args.res}x{args.res}, SH0, FLAME lbs + pose + render forward + backward (to splat parameters and "
+                        f"FLAME deltas) per frame",
             "frames_in_ring": N_RING,
             "l2_policy": f"ring of {N_RING} distinct frames (inputs+workspaces ~45 MB each > 126 MB L2 in total)",
             "parallelism": f"frames sharded one per GPU (dp{args.gpus}); per step one exchange of the flat gradient bucket "

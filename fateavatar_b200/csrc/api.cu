@@ -59,19 +59,23 @@ int fs_tuning(const char* env_name, int default_value) {
 }
 
 // ---- per-stage profiling ----------------------------------------------------------------------------------
+// Developer / bench instrumentation (fs_profile_enable): process-wide, guarded by one mutex; events are kept per device.
+#include <mutex>
 #include <vector>
 namespace {
 struct ProfRec {
-    int stage;
+    int stage, device;
     cudaEvent_t start, stop;
 };
-bool g_prof_on = false;
+std::atomic<bool> g_prof_on{false};
+std::mutex g_prof_mu;
 std::vector<ProfRec> g_prof;
-std::vector<cudaEvent_t> g_event_pool;
-cudaEvent_t prof_event() {
-    if (!g_event_pool.empty()) {
-        cudaEvent_t e = g_event_pool.back();
-        g_event_pool.pop_back();
+std::vector<cudaEvent_t> g_event_pool[64];
+cudaEvent_t prof_event(int dev) {  // g_prof_mu held
+    auto& pool = g_event_pool[dev & 63];
+    if (!pool.empty()) {
+        cudaEvent_t e = pool.back();
+        pool.pop_back();
         return e;
     }
     cudaEvent_t e;
@@ -81,14 +85,19 @@ cudaEvent_t prof_event() {
 }  // namespace
 
 FsStageTimer::FsStageTimer(int stage, cudaStream_t st) : slot(-1), stream(st) {
-    if (!g_prof_on) return;
-    ProfRec r{stage, prof_event(), prof_event()};
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    ProfRec r{stage, dev, prof_event(dev), prof_event(dev)};
     cudaEventRecord(r.start, stream);
     g_prof.push_back(r);
     slot = (int)g_prof.size() - 1;
 }
 FsStageTimer::~FsStageTimer() {
-    if (slot >= 0) cudaEventRecord(g_prof[slot].stop, stream);
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    if (slot < (int)g_prof.size()) cudaEventRecord(g_prof[slot].stop, stream);
 }
 
 int fs_num_sms() {  // per device: a process may drive more than one GPU
@@ -328,13 +337,14 @@ int fs_knn_mean_dist2(int P, const float* d_points, float* d_mean_dist2, void* d
 void fs_set_tile_hint(uint32_t max_tile_instances) { g_tile_hint = max_tile_instances; }
 void fs_set_early_notify(int on) { g_early_notify = on != 0; }
 
-void fs_profile_enable(int on) { g_prof_on = on != 0; }
+void fs_profile_enable(int on) { g_prof_on.store(on != 0); }
 
 int fs_profile_read(float* total_ms, int* counts, int n) {
     for (int i = 0; i < n; ++i) {
         total_ms[i] = 0.0f;
         counts[i] = 0;
     }
+    std::lock_guard<std::mutex> lock(g_prof_mu);
     for (auto& r : g_prof) {
         if (cudaEventSynchronize(r.stop) != cudaSuccess) {
             fs_set_error("fs_profile_read: event sync failed");
@@ -346,8 +356,8 @@ int fs_profile_read(float* total_ms, int* counts, int n) {
             total_ms[r.stage] += ms;
             counts[r.stage] += 1;
         }
-        g_event_pool.push_back(r.start);
-        g_event_pool.push_back(r.stop);
+        g_event_pool[r.device & 63].push_back(r.start);
+        g_event_pool[r.device & 63].push_back(r.stop);
     }
     g_prof.clear();
     return FS_OK;

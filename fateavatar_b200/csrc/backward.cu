@@ -1,23 +1,16 @@
-// Backward of the splat render: blend backward (per tile) + fused per-Gaussian backward.
+// Backward of the splat render: the fused per-Gaussian backward and the launcher of the two backward kernels.
 //
-// Replaces DGR cuda_rasterizer/backward.cu:399-557 (renderCUDA bwd), :144-274 (computeCov2DCUDA),
-// :346-396 (preprocessCUDA bwd) [+ :20-139 SH, :278-341 cov3D] and the nine torch::zeros of
-// rasterize_points.cu:151-159.
+// Replaces DGR cuda_rasterizer/backward.cu:144-274 (computeCov2DCUDA), :346-396 (preprocessCUDA bwd) [+ :20-139 SH,
+// :278-341 cov3D] and the nine torch::zeros of rasterize_points.cu:151-159.  The blend backward (renderCUDA bwd,
+// backward.cu:399-557) is backward_pipe.cu.
 //
 // The hand-derived gradient keeps the reference's deviations from "autograd of the forward":
-// no zeroing at the alpha = 0.99 clamp, T recovered by division, 1/(det^2 + 1e-7), frustum-clamp masks only
-// on dL/dt.x, dL/dt.y, no quaternion-normalisation Jacobian, SH clamp via the saved flags, and pixels skip
-// instances at positions >= n_contrib.
+// no zeroing at the alpha = 0.99 clamp, 1/(det^2 + 1e-7), frustum-clamp masks only on dL/dt.x, dL/dt.y, no
+// quaternion-normalisation Jacobian, SH clamp via the saved flags, and pixels skip instances at positions >= n_contrib.
 //
-// B200 design of the blend backward (the dominant training kernel):
-//   * same tiling as the forward: sorted 48-byte records streamed back-to-front with cp.async.bulk + mbarrier,
-//     8x4 pixels per warp, ballot culling against the alpha >= 1/255 bounding box;
-//   * the reference issues 9 global float atomics per contributing (pixel, Gaussian) pair.  Here the 9 partial
-//     derivatives are butterfly-reduced over the warp, summed over the CTA's 8 warps in shared memory, and
-//     flushed once per (tile, Gaussian) with three 128-bit vector reductions (red.global.add.v4.f32) into a
-//     48-byte per-Gaussian accumulator -- ~100x fewer L2 atomic operations;
-//   * the per-Gaussian kernel consumes that accumulator and writes every API gradient exactly once, so no
-//     output tensor needs a zero-fill.
+// The blend backward leaves nine sums per Gaussian in a 48-byte accumulator (grad_acc, three red.global.add.v4.f32
+// worth of data per (block, Gaussian)); the per-Gaussian kernel below consumes it and writes every API gradient
+// exactly once, so no output tensor needs a zero-fill.
 #include "common.cuh"
 
 namespace {
@@ -30,283 +23,6 @@ __device__ const float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.
                                    0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
                                    -0.5900435899266435f};
 
-
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
-// One step of a transposing warp reduction: N live values -> N/2, pairing lanes that differ in bit OFF.
-// The lane with the bit set keeps the upper half.  After steps 16, 8, 4 on 32 values every lane holds the
-// 4 values {i + (lane & 28)}, summed over its 8-lane class; two plain xor steps finish the sum.
-template <int OFF, int N>
-__device__ __forceinline__ void treduce_step(float* v, int lane) {
-    const bool up = (lane & OFF) != 0;
-#pragma unroll
-    for (int i = 0; i < N / 2; ++i) {
-        const float send = up ? v[i] : v[i + N / 2];
-        const float keep = up ? v[i + N / 2] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
-    }
-}
-
-constexpr int kGroup = 4;
-
-// grad_acc layout per Gaussian (12 floats): [0]=dmean2D.x [1]=dmean2D.y [2]=dconic.x [3]=dconic.y
-//                                           [4]=dconic.w  [5]=dopacity  [6..8]=dcolor rgb  [9..11]=0
-constexpr int kWarps = 8;   // independent warps per CTA
-constexpr int kBatch = 64;  // records per stage
-struct WarpStage {
-    SplatRec rec[2][kBatch];
-};
-
-// Persistent warps pull (tile, depth segment, 8x4 block) units from an atomic work counter.  A depth segment is
-// FS_SEG consecutive positions of the tile's sorted list; the forward kernel left, for every pixel, the
-// transmittance and the colour accumulated behind each segment boundary (ckpt), so a unit can start its
-// back-to-front walk at its own segment instead of at the end of the list.  This bounds the serial chain of a
-// unit (the critical path when a dense tile's whole list belonged to one warp) and multiplies the number of
-// units available to keep every SM sub-partition busy.
-#ifndef FS_BWD_MIN_CTAS
-#define FS_BWD_MIN_CTAS 1
-#endif
-__global__ void __launch_bounds__(kWarps * 32, FS_BWD_MIN_CTAS)
-blend_backward_kernel(const uint4* __restrict__ tile_meta, const uint2* __restrict__ seg_info,
-                      const float4* __restrict__ ckpt,
-                      const float4* __restrict__ final_C,
-                      const uint32_t* __restrict__ n_segments, uint32_t sm_count,
-                      uint32_t* __restrict__ sm_slots, uint32_t* __restrict__ work_counter,
-                      const SplatRec* __restrict__ inst_splat, int W, int H, const float* __restrict__ bg_color,
-                      const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
-                      const float* __restrict__ dL_dpix, float* __restrict__ grad_acc, uint32_t Rcap) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    WarpStage* stages = reinterpret_cast<WarpStage*>(smem_raw);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sizeof(WarpStage) * kWarps);
-
-    fs::pdl_trigger();  // the per-Gaussian kernel may begin launching; it waits for this grid before reading
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    {   // keep ~2 dense units per active warp (see blend_forward.cu); surplus CTAs retire immediately
-        const uint32_t dense_units = __ldg(n_segments) * 8u;
-        const uint32_t want_per_sm = max(1u, dense_units / (2u * kWarps * sm_count));
-        // placement-independent: the k-th CTA to arrive on an SM stays iff k < want_per_sm
-        __shared__ uint32_t s_rank;
-        if (threadIdx.x == 0) {
-            uint32_t smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            s_rank = atomicAdd(&sm_slots[smid & 255u], 1u);
-        }
-        __syncthreads();
-        if (s_rank >= want_per_sm) return;
-    }
-    SplatRec(*rec_ring)[kBatch] = stages[wid].rec;
-    uint64_t* s_full = bars + wid * 2;
-    if (lane == 0) {
-        fs::mbar_init(&s_full[0], 1);
-        fs::mbar_init(&s_full[1], 1);
-        fs::mbar_fence_init();
-    }
-    __syncwarp();
-    uint32_t fills = 0;
-
-    const int gx = (W + FS_TILE - 1) / FS_TILE;
-    const float bg0 = __ldg(bg_color), bg1 = __ldg(bg_color + 1), bg2 = __ldg(bg_color + 2);
-    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
-    const uint32_t n_units = __ldg(n_segments) * 8u;
-    const size_t plane = (size_t)H * W;
-
-    for (;;) {
-        uint32_t unit = 0;
-        if (lane == 0) unit = atomicAdd(work_counter, 1u);
-        unit = __shfl_sync(0xffffffffu, unit, 0);
-        if (unit >= n_units) break;
-        const uint2 sg = seg_info[unit >> 3];
-        const int tile = (int)sg.x;
-        const uint32_t seg_lo = sg.y * FS_SEG;
-        const int blk = (int)(unit & 7u);
-        const int tile_x = tile % gx, tile_y = tile / gx;
-        const int bx = tile_x * FS_TILE + (blk & 1) * 8, by = tile_y * FS_TILE + (blk >> 1) * 4;
-        const int px = bx + (lane & 7), py = by + (lane >> 3);
-        const bool inside = px < W && py < H;
-        const float pxf = (float)px, pyf = (float)py;
-        const float wx0 = (float)bx, wx1 = (float)min(bx + 7, W - 1), wy0 = (float)by, wy1 = (float)min(by + 3, H - 1);
-
-        const uint4 meta = tile_meta[tile];
-        uint2 range = make_uint2(meta.x, meta.y);
-        if (range.y > Rcap) range = make_uint2(0u, 0u);
-
-        const size_t pid = (size_t)py * W + px;
-        const float T_final = inside ? final_T[pid] : 0.0f;
-        const uint32_t last_contributor = inside ? n_contrib[pid] : 0u;
-        float dpx = 0.f, dpy = 0.f, dpz = 0.f;
-        if (inside) {
-            dpx = dL_dpix[pid];
-            dpy = dL_dpix[plane + pid];
-            dpz = dL_dpix[2 * plane + pid];
-        }
-        const float bg_dot = bg0 * dpx + bg1 * dpy + bg2 * dpz;
-
-        // this unit walks positions [seg_lo, seg_hi) back to front; positions >= the block's largest n_contrib
-        // are never visited, so the stream starts at min(seg_hi, that)
-        const uint32_t seg_hi = min(seg_lo + FS_SEG, range.y - range.x);
-        uint32_t wl = last_contributor;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) wl = max(wl, __shfl_xor_sync(0xffffffffu, wl, o));
-        const uint32_t warp_last = min(wl, seg_hi);
-        const int nbatches = warp_last > seg_lo ? (int)((warp_last - seg_lo + kBatch - 1) / kBatch) : 0;
-
-        // batch k covers positions [lo_k, lo_k + cnt_k), walking down from warp_last to seg_lo
-        auto batch_lo = [&](int k) { return (uint32_t)max((int)seg_lo, (int)warp_last - (k + 1) * kBatch); };
-        auto batch_cnt = [&](int k) { return (warp_last - (uint32_t)k * kBatch) - batch_lo(k); };
-        auto issue = [&](int k) {  // lane 0 only
-            const uint32_t bytes = batch_cnt(k) * (uint32_t)sizeof(SplatRec);
-            const uint32_t s = (fills + (uint32_t)k) & 1u;
-            fs::mbar_expect_tx(&s_full[s], bytes);
-            fs::bulk_g2s(&rec_ring[s][0], inst_splat + range.x + batch_lo(k), bytes, &s_full[s]);
-        };
-        if (lane == 0 && nbatches > 0) issue(0);
-
-        float T = T_final;
-        float ar0 = 0.f, ar1 = 0.f, ar2 = 0.f;  // accum_rec
-        float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;  // last_color
-        float last_alpha = 0.f;
-        if (last_contributor > seg_hi) {
-            // the pixel's list continues behind this segment: resume from the forward kernel's checkpoint
-            const float4 c4 = ckpt[((size_t)meta.z + sg.y + 1) * FS_TILE_PIX +
-                                   ((by - tile_y * FS_TILE) + (lane >> 3)) * FS_TILE + (bx - tile_x * FS_TILE) + (lane & 7)];
-            const float4 fc = final_C[pid];
-            const float inv = __fdividef(1.0f, c4.x);
-            T = c4.x;
-            ar0 = (fc.x - c4.y) * inv;  // colour accumulated behind the boundary
-            ar1 = (fc.y - c4.z) * inv;
-            ar2 = (fc.z - c4.w) * inv;
-        }
-
-        for (int kb = 0; kb < nbatches; ++kb) {
-            __syncwarp();
-            if (lane == 0 && kb + 1 < nbatches) issue(kb + 1);
-            const uint32_t f = fills + (uint32_t)kb;
-            fs::mbar_wait(&s_full[f & 1u], (f >> 1) & 1u);
-            const SplatRec* rec = rec_ring[f & 1u];
-            const uint32_t lo = batch_lo(kb);
-            const int cnt = (int)batch_cnt(kb);
-            for (int cb = ((cnt - 1) >> 5) << 5; cb >= 0; cb -= 32) {
-                const int j = cb + lane;
-                bool hit = false;
-                if (j < cnt) {
-                    const float4 q0 = rec[j].q0;
-                    hit = !(q0.z < 0.0f) &&
-                          !(q0.x + q0.z < wx0 || q0.x - q0.z > wx1 || q0.y + q0.w < wy0 || q0.y - q0.w > wy1);
-                }
-                unsigned m = __ballot_sync(0xffffffffu, hit);
-                while (m) {
-                    // four survivors per round, back to front
-                    int jj[kGroup];
-                    bool live[kGroup];
-#pragma unroll
-                    for (int k = 0; k < kGroup; ++k) {  // branch-free extraction, highest set bit first
-                        const int bit = 31 - __clz(m);    // -1 when m == 0
-                        live[k] = bit >= 0;
-                        jj[k] = live[k] ? cb + bit : cb;
-                        m &= ~(live[k] ? (1u << bit) : 0u);
-                    }
-                    // independent part: power, G, alpha for the four survivors
-                    float G[kGroup], alpha[kGroup], dx[kGroup], dy[kGroup], inv[kGroup];
-                    float4 q1[kGroup], q2[kGroup];
-                    bool ok[kGroup];
-                    bool any_ok = false;
-#pragma unroll
-                    for (int k = 0; k < kGroup; ++k) {
-                        const int r = jj[k];
-                        const float4 q0 = rec[r].q0;
-                        q1[k] = rec[r].q1;
-                        q2[k] = rec[r].q2;
-                        dx[k] = fs::sub(q0.x, pxf);
-                        dy[k] = fs::sub(q0.y, pyf);
-                        const float power = fs::splat_power(dx[k], dy[k], q1[k].x, q1[k].y, q1[k].z);
-                        G[k] = expf(power);
-                        alpha[k] = fminf(0.99f, fs::mul(q1[k].w, G[k]));
-                        ok[k] = live[k] && (lo + (uint32_t)r) < last_contributor && power <= 0.0f &&
-                                alpha[k] >= 1.0f / 255.0f;
-                        inv[k] = __fdividef(1.0f, 1.0f - alpha[k]);
-                        any_ok |= ok[k];
-                    }
-                    if (!__any_sync(0xffffffffu, any_ok)) continue;
-                    // sequential part: transmittance and the running "colour behind" recurrence
-                    float Tk[kGroup], a0[kGroup], a1[kGroup], a2[kGroup];
-#pragma unroll
-                    for (int k = 0; k < kGroup; ++k) {
-                        {   // predicated: no branches inside the dependent chain
-                            const float oml = 1.0f - last_alpha;
-                            const float n0 = last_alpha * lc0 + oml * ar0;
-                            const float n1 = last_alpha * lc1 + oml * ar1;
-                            const float n2 = last_alpha * lc2 + oml * ar2;
-                            T = ok[k] ? T * inv[k] : T;
-                            ar0 = ok[k] ? n0 : ar0;
-                            ar1 = ok[k] ? n1 : ar1;
-                            ar2 = ok[k] ? n2 : ar2;
-                            lc0 = ok[k] ? q2[k].x : lc0;
-                            lc1 = ok[k] ? q2[k].y : lc1;
-                            lc2 = ok[k] ? q2[k].z : lc2;
-                            last_alpha = ok[k] ? alpha[k] : last_alpha;
-                        }
-                        Tk[k] = T;
-                        a0[k] = ar0;
-                        a1[k] = ar1;
-                        a2[k] = ar2;
-                    }
-                    // independent part: the nine partial derivatives per survivor
-                    float v[32], e[kGroup];
-#pragma unroll
-                    for (int k = 0; k < kGroup; ++k) {
-                        const float w = ok[k] ? 1.0f : 0.0f;
-                        const float dchannel_dcolor = alpha[k] * Tk[k] * w;
-                        float dL_dalpha = ((q2[k].x - a0[k]) * dpx + (q2[k].y - a1[k]) * dpy + (q2[k].z - a2[k]) * dpz) * Tk[k];
-                        dL_dalpha += (-T_final * inv[k]) * bg_dot;
-                        dL_dalpha *= w;
-                        const float dL_dG = q1[k].w * dL_dalpha;
-                        const float gdx = G[k] * dx[k], gdy = G[k] * dy[k];
-                        const float dG_ddelx = -gdx * q1[k].x - gdy * q1[k].y;
-                        const float dG_ddely = -gdy * q1[k].z - gdx * q1[k].y;
-                        v[k * 8 + 0] = dL_dG * dG_ddelx * ddelx_dx;
-                        v[k * 8 + 1] = dL_dG * dG_ddely * ddely_dy;
-                        v[k * 8 + 2] = -0.5f * gdx * dx[k] * dL_dG;
-                        v[k * 8 + 3] = -0.5f * gdx * dy[k] * dL_dG;
-                        v[k * 8 + 4] = -0.5f * gdy * dy[k] * dL_dG;
-                        v[k * 8 + 5] = G[k] * dL_dalpha;
-                        v[k * 8 + 6] = dchannel_dcolor * dpx;
-                        v[k * 8 + 7] = dchannel_dcolor * dpy;
-                        e[k] = dchannel_dcolor * dpz;
-                    }
-                    // transposing warp reduction: 36 values x 32 lanes in 42 shuffles (naive: 180)
-                    treduce_step<16, 32>(v, lane);
-                    treduce_step<8, 16>(v, lane);
-                    treduce_step<4, 8>(v, lane);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        v[i] += __shfl_xor_sync(0xffffffffu, v[i], 2);
-                        v[i] += __shfl_xor_sync(0xffffffffu, v[i], 1);
-                    }
-                    treduce_step<16, 4>(e, lane);
-                    treduce_step<8, 2>(e, lane);
-                    e[0] += __shfl_xor_sync(0xffffffffu, e[0], 4);
-                    e[0] += __shfl_xor_sync(0xffffffffu, e[0], 2);
-                    e[0] += __shfl_xor_sync(0xffffffffu, e[0], 1);
-                    // lane (l & 3) == 0 owns values {(l & 28) .. +3} = survivor l>>3, half (l>>2)&1;
-                    // lane (l & 7) == 0 also owns that survivor's ninth value
-                    const int ks = lane >> 3;
-                    const int js = ks == 0 ? jj[0] : ks == 1 ? jj[1] : ks == 2 ? jj[2] : jj[3];
-                    const bool ls = ks == 0 ? live[0] : ks == 1 ? live[1] : ks == 2 ? live[2] : live[3];
-                    if ((lane & 3) == 0 && ls) {
-                        const uint32_t g = __float_as_uint(rec[js].q2.w);
-                        float* dst = grad_acc + (size_t)g * 12;
-                        if (v[0] != 0.f || v[1] != 0.f || v[2] != 0.f || v[3] != 0.f)
-                            red_add_v4(dst + ((lane >> 2) & 1) * 4, v[0], v[1], v[2], v[3]);
-                        if ((lane & 7) == 0 && e[0] != 0.f) atomicAdd(dst + 8, e[0]);
-                    }
-                }
-            }
-        }
-        fills += (uint32_t)nbatches;
-    }
-}
 
 // ---- fused per-Gaussian backward (cov2D -> cov3D -> scale/rot, projection, SH) -----------------------------
 __global__ void __launch_bounds__(256)
@@ -542,26 +258,9 @@ void fs_launch_backward(int P, int D, int M, const float* bg, int W, int H, cons
     float* grad_acc = reinterpret_cast<float*>(ws + L.grad_acc);
     // work counter (256-byte slot) and the per-Gaussian accumulator are contiguous: one memset node
     cudaMemsetAsync(ws + L.bwd_counter, 0, (L.grad_acc - L.bwd_counter) + (size_t)P * 48, stream);
-    if (fs_tuning("FATESPLAT_BWD_PIPE", 1)) {  // lanes own splats (backward_pipe.cu); 0 = lanes own pixels (below)
+    {
         FsStageTimer timer(FS_STAGE_BLEND_BWD, stream);
         fs_launch_blend_backward_pipe(W, H, bg, ws, L, dL_dpix, grad_acc, stream);
-    } else {
-        FsStageTimer timer(FS_STAGE_BLEND_BWD, stream);
-        const size_t smem = sizeof(WarpStage) * kWarps + sizeof(uint64_t) * 2 * kWarps;
-        static std::atomic<unsigned long long> attr_set{0};
-        if (fs_first_use_on_device(attr_set))
-            cudaFuncSetAttribute(blend_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        auto* info = reinterpret_cast<fs_frame_info*>(ws + L.info);
-        const int ctas_per_sm = fs_tuning("FATESPLAT_BWD_CTAS_PER_SM", 2);  // upper bound (100 regs/thread)
-        const int grid = fs_num_sms() * ctas_per_sm;
-        blend_backward_kernel<<<grid, kWarps * 32, smem, stream>>>(
-            reinterpret_cast<const uint4*>(ws + L.tile_meta), reinterpret_cast<const uint2*>(ws + L.seg_info),
-            reinterpret_cast<const float4*>(ws + L.ckpt),
-            reinterpret_cast<const float4*>(ws + L.final_C), &info->reserved[2], (uint32_t)fs_num_sms(), reinterpret_cast<uint32_t*>(ws + L.bwd_counter + 256),
-            reinterpret_cast<uint32_t*>(ws + L.bwd_counter),
-            reinterpret_cast<const SplatRec*>(ws + L.inst_splat), W, H, bg,
-            reinterpret_cast<const float*>(ws + L.final_T), reinterpret_cast<const uint32_t*>(ws + L.n_contrib),
-            dL_dpix, grad_acc, (uint32_t)L.instance_capacity);
     }
     const float h_y = H / (2.0f * tan_fovy);
     const float h_x = W / (2.0f * tan_fovx);

@@ -4,10 +4,11 @@
 // skips positions >= n_contrib, power > 0, alpha < 1/255; no zeroing at the 0.99 clamp), same nine sums per
 // Gaussian, written into the same 48-byte accumulator that preprocess_backward_kernel (backward.cu) consumes.
 //
-// Why: with lanes owning pixels (backward.cu: blend_backward_kernel) every surviving (block, splat) pair ends in a
-// 36-value x 32-lane transposing reduction -- 42 shuffles and ~60 selects/adds, ~38 % of that kernel's
-// instructions.  Here a lane keeps ONE splat for 32 consecutive steps and sees the block's 32 pixels one after
-// the other, so the nine sums accumulate in the lane's own registers and no cross-lane reduction exists at all.
+// Why: with lanes owning pixels (the reference's layout, and this repo's round-1 kernel) every (block, splat) pair ends
+// in a cross-lane sum of nine values -- nine global atomics per pixel in the reference, a 36-value x 32-lane
+// transposing reduction (42 shuffles, ~60 selects/adds, ~38 % of all instructions) in round 1.  Here a lane keeps ONE
+// splat for 32 consecutive steps and sees the block's 32 pixels one after the other, so the nine sums accumulate in
+// the lane's own registers and no cross-lane reduction exists at all.
 //
 //   * Schedule.  At step t lane l works on pixel (t - l) mod 32.  A pixel's running state (transmittance T and
 //     the colour S accumulated in front of it) is handed from lane l to lane l+1 by one rotate (4 shuffles per
@@ -24,8 +25,9 @@
 //   * Which pairs.  The forward blend left, per (block, list position), the 32-bit mask of the pixels that blended
 //     the instance (pair_mask).  A splat enters the pipeline iff its mask is non-zero and a pair contributes iff
 //     its bit is set: the backward never re-derives (and can never disagree with) the forward's decisions.
-//   * Work units (tile, depth segment, block) from the atomic work counter and the cp.async.bulk (UBLKCP) record
-//     stream are those of backward.cu; selected records are compacted into a per-warp queue in shared memory that
+//   * Work units are (tile, depth segment of FS_SEG list positions, 8x4 block), pulled from an atomic work counter by
+//     persistent warps (full segments first, binning.cu); the tile's sorted 48-byte records arrive by cp.async.bulk
+//     (UBLKCP) into a per-warp 2-stage ring guarded by mbarriers; selected records are compacted into a per-warp queue in shared memory that
 //     runs on across units (three pixel tables rotate; a table is reused once every splat that refers to it has
 //     left the pipeline).
 #include "common.cuh"
@@ -163,7 +165,7 @@ __device__ __forceinline__ void run_window(Pipe& P, WarpSmem* ws, const SplatRec
 }
 
 // Sums of the batch that left the pipeline during the last window -> the per-Gaussian accumulator.
-// Layout (backward.cu): [0]=dmean2D.x [1]=dmean2D.y [2]=dconic.x [3]=dconic.y [4]=dconic.w [5]=dopacity [6..8]=dcolor
+// Layout (consumed by backward.cu): [0]=dmean2D.x [1]=dmean2D.y [2]=dconic.x [3]=dconic.y [4]=dconic.w [5]=dopacity [6..8]=dcolor
 __device__ __forceinline__ void flush_batch(const WarpSmem* ws, uint32_t slot0, int lane, float* __restrict__ grad_acc,
                                             float ddelx_dx, float ddely_dy) {
     const SplatRec* pr = &ws->queue[slot0 + lane];
@@ -194,7 +196,7 @@ blend_backward_pipe_kernel(const uint4* __restrict__ tile_meta, const uint2* __r
     extern __shared__ __align__(128) unsigned char smem_raw[];
     fs::pdl_trigger();  // the per-Gaussian kernel may begin launching; it waits for this grid before reading
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    {   // same placement-independent CTA budget as backward.cu / blend_forward.cu
+    {   // same placement-independent CTA budget as blend_forward.cu
         const uint32_t dense_units = __ldg(n_segments) * 8u;
         const uint32_t want_per_sm = max(1u, dense_units / (2u * kWarps * sm_count));
         __shared__ uint32_t s_rank;
