@@ -337,6 +337,35 @@ def bench_extras(args, dev, torch):
             c1["cpu_port_error"] = repr(ex)[:200]
         out["config1"] = c1
 
+        # ---- config 2, the rasterizer alone (north_star: >= 5x the compiled reference at 512^2 / ~100k Gaussians) ----
+        try:
+            from fateavatar_b200 import graph as fgraph
+
+            sc = scenes.head_scene()
+            t = scenes.to_torch(sc, dev)
+            rs2 = settings(t, t["camera"], sc["sh_degree"])
+            dp2 = torch.randn(3, t["camera"]["H"], t["camera"]["W"], device=dev)
+            fwd = lambda: R.forward_raw(rs2, t["means3D"], t["shs"], None, t["opacities"], t["scales"], t["rotations"], None)
+            capf = fgraph.CapturedStep(lambda _i: (fwd(), {})[1], {}, params=(), warmup=2, device=dev)
+            R.set_async(True)
+            capfb = fgraph.CapturedStep(lambda _i: (R.backward_raw(fwd()[2], dp2), {})[1], {}, params=(), warmup=2, device=dev)
+            R.set_async(True)
+            c2 = {"what": "scenes.head_scene(): 100k splats on the head-sized shell, 512x512, SH0; fs_forward / fs_forward + "
+                          "fs_backward replayed from a CUDA graph (device time, events) against the compiled reference's "
+                          "rasterize_gaussians(_backward) (wall clock with synchronisation: it blocks on num_rendered itself)",
+                  "new_fwd_ms": ev_ms(capf.graph.replay, warm=5, iters=100),
+                  "new_fwdbwd_ms": ev_ms(capfb.graph.replay, warm=5, iters=100)}
+            capf.check(), capfb.check()
+            if ref is not None:
+                a = ref_args(t, t["camera"], sc["sh_degree"])
+                c2["gpu_reference_fwd_ms"] = wall_ms(lambda: ref.rasterize_gaussians(*a), warm=5, iters=30)
+                c2["gpu_reference_fwdbwd_ms"] = wall_ms(lambda: ref_fwd_bwd(a, dp2), warm=5, iters=30)
+                c2["speedup_fwd"] = c2["gpu_reference_fwd_ms"] / c2["new_fwd_ms"]
+                c2["speedup_fwdbwd"] = c2["gpu_reference_fwdbwd_ms"] / c2["new_fwdbwd_ms"]
+            out["config2_rasterizer"] = c2
+        except Exception as ex:
+            out["config2_rasterizer"] = {"error": repr(ex)[:300]}
+
         # ---- config 5 ----
         sc = scenes.stress_scene(view=0)
         t = scenes.to_torch(sc, dev)
@@ -852,7 +881,16 @@ def main():
             return float(out["loss"][0])
         api = "graph.CapturedStep replaying avatar.forward_frame + L1 loss + backward; dense NCCL all-reduce per leaf"
 
+    if e2e_sharded is not None and e2e_sharded.ex is not None:
+        e2e_sharded.ex.timing(reset=True)
     graph_fps = time_e2e(graph_step, e2e_steps)
+    e2e_exchange_timing = None
+    if e2e_sharded is not None and e2e_sharded.ex is not None:  # device clock inside the exchange kernel, e2e steps
+        e2e_exchange_timing = dict(e2e_sharded.ex.timing(reset=True), algo=e2e_sharded.ex.algo)
+        tt = torch.tensor([e2e_exchange_timing["wait_us"], e2e_exchange_timing["work_us"]], device=dev)
+        hi = tt.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        e2e_exchange_timing.update(wait_us_max_over_ranks=float(hi[0]), work_us_max_over_ranks=float(hi[1]))
     if os.environ.get("FATESPLAT_BENCH_PROFILE") == "e2e":  # ncu --profile-from-start off: two replays of the e2e step
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
@@ -864,7 +902,7 @@ def main():
         assert len(pipe["losses"]) >= e2e_steps and all(np.isfinite(pipe["losses"])), "e2e: every step's loss must arrive"
     R.set_async(False)
     e2e = {"value": graph_fps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-           "api": api, "eager_value": eager_fps,
+           "api": api, "exchange_timing": e2e_exchange_timing, "eager_value": eager_fps,
            "eager_api": "the same step with every operator call issued from Python (default synchronous mode)"}
     params = [p_.detach() for p_ in all_leaves[:4]]
     shs = model._features_dc.detach()
