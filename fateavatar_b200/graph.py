@@ -86,9 +86,11 @@ class CapturedStep:
     def prefetch(self, host_inputs, stream):
         """Input prefetch (the pinned GT-frame prefetch of SURVEY 8f N3; upstream loads every frame synchronously,
         train/dataset.py:14-54): copy the NEXT frame's pinned host inputs into this step's static input tensors on
-        `stream` while another recorded step is still running.  The caller guarantees that this step is not in
-        flight (steps alternate between two recordings and each is waited for before it is reused)."""
+        `stream` while another recorded step is still running.  The copies are ordered on the device behind this
+        recording's previous replay (its inputs may still be in use: with two alternating recordings the prefetch for
+        step i+1 is issued while step i-1 can still be running), so the host never has to wait before calling this."""
         with torch.cuda.stream(stream):
+            stream.wait_event(self._done)  # no-op before the first replay
             for k, v in host_inputs.items():
                 self.static_in[k].copy_(v, non_blocking=True)
             ev = torch.cuda.Event()

@@ -196,6 +196,12 @@ def compare_blend(o, color, final_T=None, n_contrib=None, tol=1e-5, fragile_tol=
     res = dict(max_solid=float(d[~frag].max()) if (~frag).any() else 0.0,
                max_fragile=float(d[frag].max()) if frag.any() else 0.0, fragile_frac=float(frag.mean()))
     assert res["fragile_frac"] <= max_fragile_frac, res
+    if res["max_solid"] > tol:  # say where: the pixel, both colours, its list length and transmittance in the oracle
+        dd = np.where(frag, 0.0, d)
+        y, x = np.unravel_index(int(dd.argmax()), dd.shape)
+        res["worst_pixel"] = dict(y=int(y), x=int(x), got=np.asarray(color, np.float32)[:, y, x].tolist(),
+                                  want=o["color"][:, y, x].tolist(), n_contrib=int(o["n_contrib"][y, x]),
+                                  final_T=float(o["final_T"][y, x]), n_bad=int((dd > tol).sum()))
     assert res["max_solid"] <= tol, res
     assert res["max_fragile"] <= fragile_tol, res
     if final_T is not None:

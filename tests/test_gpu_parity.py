@@ -98,10 +98,15 @@ def test_forward_backward_vs_oracle(name, cuda_device):
 def test_very_large_tile_list_global_sort_path(cuda_device):
     """> 24576 instances in one tile: the sort falls back to global memory; results must not change."""
     sc = scenes.head_scene(P=30000, W=32, H=32, scale_mult=30.0, seed=8)
-    color, radii, st, taps, _ = run_new(sc, cuda_device)
     o = oracle_forward(orc, sc)
     assert (o["ranges"][:, 1] - o["ranges"][:, 0]).max() > 24576
+    # the backward walks ~100 depth segments per tile here (checkpoints, pair masks and the splat queue across units)
+    dpix = orc.mask_fragile(o, np.random.default_rng(5).standard_normal((3, 32, 32)).astype(np.float32))
+    color, radii, st, taps, grads = run_new(sc, cuda_device, dpix=dpix)
     check_forward_vs_oracle(color, radii, st, taps, o)
+    og = orc.backward(o, dpix)
+    for k in GRAD_NAMES:
+        assert_grad_close(k, grads[k].cpu().numpy(), og[k])
 
 
 def test_colors_precomp_cov3d_precomp_scale_modifier_black_bg(cuda_device):
