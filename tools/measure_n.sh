@@ -1,5 +1,5 @@
 #!/bin/bash
-# one multi-GPU bench line under the driver's arguments: bash tools/r2_n.sh N tag
+# one multi-GPU bench line under the driver's arguments: bash tools/measure_n.sh N tag
 mkdir -p gpurun_out
 n=$1; tag=$2
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500+n)) bench.py --gpus $n --steps 20 --warmup 5 --no-extras --no-config3 > gpurun_out/${tag}_n$n.json 2> gpurun_out/${tag}_n$n.err
