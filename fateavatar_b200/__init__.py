@@ -12,6 +12,8 @@ mirrors of the reference's interfaces for that path:
     graph.py                whole-frame CUDA-graph capture / replay (CapturedStep)
     optimizer.py, losses.py   optimise loop: fused Adam, in-place densify / prune / reset, OptimiseLoop; fused L1 image loss
     exchange.py, parallel.py  frame-sharded multi-GPU: peer-memory gradient exchange, sampler, densify sync
+    io.py                   on-disk formats of the path: the splat PLY (gaussian_model.py:190-269) and the checkpoint
+                            layout (trainer.py:396-435 / deserialize.py:7-40) over the capacity-allocated splat store
 
     import fateavatar_b200; fateavatar_b200.install()
     # from here on `import diff_gaussian_rasterization` / `from simple_knn._C import distCUDA2`

@@ -114,6 +114,26 @@ class SplatStore:
         m.num_points = P
         return m
 
+    def load_rows(self, rows):
+        """Refill the store from a checkpoint's splat attributes (io.restore_splats; train/deserialize.py:7-40): `rows`
+        maps _offset / _features_dc / _scaling / _rotation / _opacity / face_index / bary_coords to tensors with P rows.
+        As upstream, the optimizer state is not part of a checkpoint: both Adam moments and the densification statistics
+        restart from zero.  In place -- the capacity arrays are kept."""
+        P = int(rows["_offset"].shape[0])
+        if P > self.capacity:
+            raise FateSplatError(f"SplatStore capacity {self.capacity} < {P} checkpoint rows")
+        a = self.arrays()
+        for n, attr, w in FIELDS:
+            a[n][:P].copy_(rows[attr].detach().reshape(P, w))
+            a["m_" + n].zero_()
+            a["v_" + n].zero_()
+        a["face_index"][:P].copy_(rows["face_index"])
+        a["bary"][:P].copy_(rows["bary_coords"])
+        for key in ("accum", "denom", "max_radii2D", "sample_flag"):
+            a[key].zero_()
+        self.P = P
+        return self.bind()
+
     def _soa(self, k=None):
         a = self.arrays(k)
         s = FsSplatSoa()

@@ -270,3 +270,46 @@ def test_recorded_optimise_loop_tracks_the_eager_one(cuda_device):
     assert max(abs(x - y) for x, y in zip(s0, s1)) <= 0.01 * max(s0)
     assert max(abs(x - y) for x, y in zip(l0, l1)) <= 2e-3 * max(l0)
     assert l1[-1] < l1[0]  # and it optimises
+
+
+def test_checkpoint_round_trip_through_the_splat_store(cuda_device, tmp_path):
+    """io.model_state / io.restore_splats(store=) (train/trainer.py:396-435, train/deserialize.py:7-40): a checkpoint taken
+    after a densification is compact (P rows, not the store's capacity) and refills a fresh store of another size in
+    place; Adam moments and densification statistics restart, as upstream."""
+    from fateavatar_b200 import io as fio
+
+    dev, res = cuda_device, (96, 96)
+
+    class Holder(torch.nn.Module):  # a state_dict()-able view of the splat attributes
+        def __init__(self, m):
+            super().__init__()
+            for k in ("_offset", "_features_dc", "_scaling", "_rotation", "_opacity"):
+                setattr(self, k, getattr(m, k))
+            self._features_rest = torch.nn.Parameter(torch.zeros(m._offset.shape[0], 0, 3, device=dev))
+            self.register_buffer("face_index", m.face_index)
+            self.register_buffer("bary_coords", m.bary_coords)
+
+    m = _my_model(scenes.small_avatar(seed=5, N=2000), dev, res)
+    store = fopt.SplatStore(m, capacity=4000)
+    store.view("accum").uniform_(0.1, 1.0)
+    store.uv_densify(300, generator=torch.Generator(device=dev).manual_seed(1))
+    store.bind()
+    assert store.P == 2300 and m._scaling.shape[0] == 2300
+    state = fio.model_state(Holder(m))
+    assert state["_scaling"].shape == (2300, 3) and state["_scaling"].untyped_storage().nbytes() == 2300 * 3 * 4
+    path = str(tmp_path / "ck.pth")
+    torch.save({"model": state}, path)
+
+    m2 = _my_model(scenes.small_avatar(seed=6, N=1500), dev, res)
+    store2 = fopt.SplatStore(m2, capacity=5000)
+    store2.view("m_scaling").fill_(1.0)
+    base_ptr = store2.arrays()["scaling"].data_ptr()
+    h2 = Holder(m2)
+    fio.restore_splats(h2, torch.load(path)["model"], store=store2)
+    assert store2.P == 2300 and store2.model is m2 and m2.num_points == 2300
+    assert store2.arrays()["scaling"].data_ptr() == base_ptr  # in place
+    for n, attr, w in fopt.FIELDS:
+        assert torch.equal(getattr(m2, attr).detach().reshape(2300, w), getattr(m, attr).detach().reshape(2300, w)), n
+        assert not store2.arrays()["m_" + n].any() and not store2.arrays()["v_" + n].any()
+    assert torch.equal(m2.face_index, m.face_index) and torch.equal(m2.bary_coords, m.bary_coords)
+    assert not m2.xyz_gradient_accum.any() and m2.xyz_gradient_accum.shape == (2300, 1)
