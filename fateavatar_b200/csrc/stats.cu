@@ -143,7 +143,9 @@ extern "C" int fs_l1_loss(size_t n, const float* d_x, const float* d_target, flo
         fs_set_error("fs_l1_loss: invalid argument");
         return FS_ERR_INVALID_ARGUMENT;
     }
-    const int grid = (int)std::min<size_t>((n + kL1Threads * 4 - 1) / (kL1Threads * 4), 1024);
+    // two CTAs per SM: every CTA ends with one atomic on the same ticket word (~10 ns each at the L2), so the tail grows
+    // with the CTA count, not with the image
+    const int grid = (int)std::min<size_t>((n + kL1Threads * 4 - 1) / (kL1Threads * 4), (size_t)std::min(1024, 2 * fs_num_sms()));
     float* partial = static_cast<float*>(d_workspace);
     unsigned int* counter = reinterpret_cast<unsigned int*>(partial + 1024);  // zero-initialised by the caller once
     l1_loss_kernel<<<grid, kL1Threads, 0, static_cast<cudaStream_t>(stream)>>>(n, d_x, d_target, d_grad, partial, counter,
