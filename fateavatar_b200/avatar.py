@@ -134,7 +134,7 @@ def forward_frame(model, input, exact_camera=None, extras=True):
     """`exact_camera` (default: `model.exact_camera` if set, else False) selects FrameCamera(exact=True).
     `extras=False` leaves out the two outputs that only the scale / rotation regularisers read ("scale" = exp(_scaling),
     "raw_rot" = quaternion_to_axis_angle(_rotation): ~15 elementwise launches per frame) for callers whose loss does not
-    use them; everything else is computed regardless.
+    use them, `extras=("scale",)` computes only the named ones; everything else is computed regardless.
     `model`: an object with FateAvatar's attributes (flame, faces, face_index, bary_coords, face_scaling_canonical,
     _scaling, _rotation, _offset, _opacity, _features_dc, delta_shapedirs, delta_posedirs, delta_vertex, cfg_model,
     shell_len, bg_color, img_res, device); `input`: the dataset's dict (cam_pose, fovx, fovy, flame_pose, expression).
@@ -173,7 +173,12 @@ def forward_frame(model, input, exact_camera=None, extras=True):
         campos=camera.camera_center, prefiltered=False, debug=False)
     image, radii = _rasterizer.GaussianRasterizer(settings)(means3D=xyz, means2D=screenspace, shs=model._features_dc,
                                                            opacities=opac, scales=scales, rotations=rots)
-    out = {"scale": torch.exp(model._scaling), "raw_rot": quaternion_to_axis_angle(model._rotation)} if extras else {}
+    want = ("scale", "raw_rot") if extras is True else (tuple(extras) if extras else ())
+    out = {}
+    if "scale" in want:
+        out["scale"] = torch.exp(model._scaling)
+    if "raw_rot" in want:
+        out["raw_rot"] = quaternion_to_axis_angle(model._rotation)
     out.update({
         "rgb_image": image[None],
         "viewspace_points": [screenspace],

@@ -287,6 +287,8 @@ class OptimiseLoop:
         self.store = SplatStore(model, self.cfg["max_points_num"] + self.cfg["increase_num"])
         self._parallel = _parallel
         self.global_step = 0
+        self._last = None
+        self._staged_host = None
         self.recaptures = 0
         self.recording_s = 0.0  # wall clock spent (re)recording the step, for reports
         self._build()
@@ -358,9 +360,28 @@ class OptimiseLoop:
             self.adam.step()
         return {"loss": loss.detach().reshape(1)}
 
-    def step(self, host_inputs):
-        """One iteration.  Returns the pinned {"loss": [1]} of the step (valid after `wait()`)."""
+    def prefetch(self, host_inputs):
+        """Stage the pinned host inputs of the NEXT step() on a side stream (the pinned GT-frame prefetch of SURVEY 8f N3;
+        upstream loads every frame synchronously, train/dataset.py:14-54): issued right after a step() it overlaps that
+        step instead of preceding the next one.  The next call is then `step()` without arguments."""
+        self._staged_host = host_inputs
+        if self.captured is not None:
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            self.captured[self.global_step & 1].prefetch(host_inputs, self._copy_stream)
+
+    def step(self, host_inputs=None):
+        """One iteration on `host_inputs`, or on what `prefetch` staged.  Returns the pinned {"loss": [1]} of the step
+        (valid after `wait()`, or after `last.wait()` for a caller that keeps `last = loop.last` and reads one step
+        behind its launches)."""
         c, t = self.cfg, self.global_step
+        if host_inputs is None:
+            host_inputs = getattr(self, "_staged_host", None)
+            if host_inputs is None:
+                raise FateSplatError("OptimiseLoop.step(): no inputs given and nothing staged by prefetch()")
+            if self.captured is not None and self.captured[t & 1]._staged is not None:
+                host_inputs = None  # the side-stream copy into this recording is under way: replay waits for its event
+        self._staged_host = None
         if self.captured is not None:
             cap = self.captured[t & 1]
             self._parity = t & 1
@@ -394,6 +415,11 @@ class OptimiseLoop:
             self._build()
         self.global_step += 1
         return res
+
+    @property
+    def last(self):
+        """The recording the last step() replayed (None in eager mode): `last.wait()` blocks until THAT step is done."""
+        return self._last
 
     def wait(self):
         if self._last is not None:
