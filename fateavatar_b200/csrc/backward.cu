@@ -245,7 +245,7 @@ preprocess_backward_kernel(int P, int D, int M, const float* __restrict__ means3
 
 }  // namespace
 
-void fs_launch_blend_backward_pipe(int W, int H, const float* bg, char* ws, const fs_workspace_layout& L,
+void fs_launch_blend_backward_pipe(int P, int W, int H, const float* bg, char* ws, const fs_workspace_layout& L,
                                    const float* dL_dpix, float* grad_acc, cudaStream_t stream);  // backward_pipe.cu
 
 void fs_launch_backward(int P, int D, int M, const float* bg, int W, int H, const float* means3D, const float* shs,
@@ -260,7 +260,7 @@ void fs_launch_backward(int P, int D, int M, const float* bg, int W, int H, cons
     cudaMemsetAsync(ws + L.bwd_counter, 0, (L.grad_acc - L.bwd_counter) + (size_t)P * 48, stream);
     {
         FsStageTimer timer(FS_STAGE_BLEND_BWD, stream);
-        fs_launch_blend_backward_pipe(W, H, bg, ws, L, dL_dpix, grad_acc, stream);
+        fs_launch_blend_backward_pipe(P, W, H, bg, ws, L, dL_dpix, grad_acc, stream);
     }
     const float h_y = H / (2.0f * tan_fovy);
     const float h_x = W / (2.0f * tan_fovx);

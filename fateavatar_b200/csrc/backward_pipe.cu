@@ -167,10 +167,10 @@ __device__ __forceinline__ void run_window(Pipe& P, WarpSmem* ws, const SplatRec
 // Sums of the batch that left the pipeline during the last window -> the per-Gaussian accumulator.
 // Layout (consumed by backward.cu): [0]=dmean2D.x [1]=dmean2D.y [2]=dconic.x [3]=dconic.y [4]=dconic.w [5]=dopacity [6..8]=dcolor
 __device__ __forceinline__ void flush_batch(const WarpSmem* ws, uint32_t slot0, int lane, float* __restrict__ grad_acc,
-                                            float ddelx_dx, float ddely_dy) {
+                                            uint32_t n_gaussians, float ddelx_dx, float ddely_dy) {
     const SplatRec* pr = &ws->queue[slot0 + lane];
     const uint32_t id = __float_as_uint(pr->q2.w);
-    if (id == kNullId) return;
+    if (id >= n_gaussians) return;  // null splat (kNullId); also keeps a corrupt record from writing outside grad_acc
     const float4 q1 = pr->q1;
     const float4 fa = ws->finA[lane], fb = ws->finB[lane];
     const float fc = ws->finC[lane];
@@ -192,7 +192,7 @@ blend_backward_pipe_kernel(const uint4* __restrict__ tile_meta, const uint2* __r
                            const uint32_t* __restrict__ pair_mask, int W, int H,
                            const float* __restrict__ bg_color, const float* __restrict__ final_T,
                            const uint32_t* __restrict__ n_contrib, const float* __restrict__ dL_dpix,
-                           float* __restrict__ grad_acc, uint32_t Rcap) {
+                           float* __restrict__ grad_acc, uint32_t n_gaussians, uint32_t Rcap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     fs::pdl_trigger();  // the per-Gaussian kernel may begin launching; it waits for this grid before reading
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -393,7 +393,7 @@ blend_backward_pipe_kernel(const uint4* __restrict__ tile_meta, const uint2* __r
                 run_window<true>(P, ws, nxt, lane);
             else
                 run_window<false>(P, ws, nxt, lane);
-            if (prev_valid) flush_batch(ws, prev, lane, grad_acc, ddelx_dx, ddely_dy);
+            if (prev_valid) flush_batch(ws, prev, lane, grad_acc, n_gaussians, ddelx_dx, ddely_dy);
             prev = head;
             prev_valid = true;
             head = head == 64u ? 0u : head + 32u;
@@ -412,7 +412,7 @@ blend_backward_pipe_kernel(const uint4* __restrict__ tile_meta, const uint2* __r
 
 }  // namespace
 
-void fs_launch_blend_backward_pipe(int W, int H, const float* bg, char* ws, const fs_workspace_layout& L,
+void fs_launch_blend_backward_pipe(int P, int W, int H, const float* bg, char* ws, const fs_workspace_layout& L,
                                    const float* dL_dpix, float* grad_acc, cudaStream_t stream) {
     const size_t smem = sizeof(WarpSmem) * kWarps + sizeof(uint64_t) * 2 * kWarps;
     static std::atomic<unsigned long long> attr_set{0};
@@ -428,5 +428,5 @@ void fs_launch_blend_backward_pipe(int W, int H, const float* bg, char* ws, cons
         reinterpret_cast<uint32_t*>(ws + L.bwd_counter), reinterpret_cast<const SplatRec*>(ws + L.inst_splat),
         reinterpret_cast<const uint32_t*>(ws + L.pair_mask), W, H, bg,
         reinterpret_cast<const float*>(ws + L.final_T), reinterpret_cast<const uint32_t*>(ws + L.n_contrib), dL_dpix,
-        grad_acc, (uint32_t)L.instance_capacity);
+        grad_acc, (uint32_t)P, (uint32_t)L.instance_capacity);
 }

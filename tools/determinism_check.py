@@ -21,6 +21,10 @@ def once(t, sc, dpix):
     g = R.backward_raw(st, dpix)
     out.update({k: v.clone() for k, v in zip(GRAD_NAMES, g)})
     torch.cuda.synchronize()
+    # the backward must leave every forward output alone (a stray reduction would land in one of them)
+    assert torch.equal(color, out["color"]) and torch.equal(radii, out["radii"]), "backward modified a forward output"
+    for k in ("final_T", "n_contrib", "point_list", "ranges"):
+        assert torch.equal(taps[k], out[k]), f"backward modified {k}"
     return out
 
 def main():
