@@ -18,7 +18,6 @@ struct AdamTable {
     float* v[FS_ADAM_MAX_TENSORS];
     unsigned long long n[FS_ADAM_MAX_TENSORS];
     float lr[FS_ADAM_MAX_TENSORS];
-    unsigned char vec[FS_ADAM_MAX_TENSORS];  // all four arrays 16-byte aligned
     unsigned int first_chunk[FS_ADAM_MAX_TENSORS + 1];
     int count;
 };
@@ -48,36 +47,18 @@ adam_kernel(const AdamTable t, int* __restrict__ steps, double beta1d, double be
     float* __restrict__ m = t.m[k];
     float* __restrict__ v = t.v[k];
     const size_t n = t.n[k];
-    auto update = [&](float gi, float& pi, float& mi, float& vi) {  // the same fp32 sequence for every element
-        mi = mi + w1 * (gi - mi);
-        vi = vi * beta2 + (w2 * gi) * gi;
-        const float denom = sqrtf(vi) / bc2_sqrt + eps;
-        pi = pi + (-step_size) * (mi / denom);
-    };
-    // a thread owns kAdamPerThread = 4 consecutive elements: one 128-bit access per array when the tensor allows it
-    const size_t i0 = base + (size_t)threadIdx.x * kAdamPerThread;
-    if (t.vec[k] && i0 + kAdamPerThread <= n) {
-        const float4 g4 = *reinterpret_cast<const float4*>(g + i0);
-        float4 p4 = *reinterpret_cast<float4*>(p + i0), m4 = *reinterpret_cast<float4*>(m + i0),
-               v4 = *reinterpret_cast<float4*>(v + i0);
-        update(g4.x, p4.x, m4.x, v4.x);
-        update(g4.y, p4.y, m4.y, v4.y);
-        update(g4.z, p4.z, m4.z, v4.z);
-        update(g4.w, p4.w, m4.w, v4.w);
-        *reinterpret_cast<float4*>(p + i0) = p4;
-        *reinterpret_cast<float4*>(m + i0) = m4;
-        *reinterpret_cast<float4*>(v + i0) = v4;
-    } else {
 #pragma unroll
-        for (int u = 0; u < kAdamPerThread; ++u) {
-            const size_t i = i0 + u;
-            if (i < n) {
-                float pi = p[i], mi = m[i], vi = v[i];
-                update(g[i], pi, mi, vi);
-                p[i] = pi;
-                m[i] = mi;
-                v[i] = vi;
-            }
+    for (int u = 0; u < kAdamPerThread; ++u) {
+        const size_t i = base + (size_t)u * kAdamThreads + threadIdx.x;
+        if (i < n) {
+            const float gi = g[i];
+            float mi = m[i], vi = v[i];
+            mi = mi + w1 * (gi - mi);
+            vi = vi * beta2 + (w2 * gi) * gi;
+            const float denom = sqrtf(vi) / bc2_sqrt + eps;
+            p[i] = p[i] + (-step_size) * (mi / denom);
+            m[i] = mi;
+            v[i] = vi;
         }
     }
     __syncthreads();
@@ -259,8 +240,6 @@ extern "C" int fs_adam_step(int n_tensors, const fs_adam_tensor* h_tensors, int*
         t.v[k] = d.exp_avg_sq;
         t.n[k] = d.n;
         t.lr[k] = d.lr;
-        t.vec[k] = ((reinterpret_cast<uintptr_t>(d.param) | reinterpret_cast<uintptr_t>(d.grad) |
-                     reinterpret_cast<uintptr_t>(d.exp_avg) | reinterpret_cast<uintptr_t>(d.exp_avg_sq)) & 15u) == 0;
         t.first_chunk[k] = chunks;
         chunks += (unsigned int)((d.n + kAdamChunk - 1) / kAdamChunk);
     }
