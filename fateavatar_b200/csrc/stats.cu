@@ -7,13 +7,21 @@
 #include "common.cuh"
 
 namespace {
+// torch.norm(grad[:, :2], dim=-1) (model/fateavatar.py:734-737) evaluates sqrt(x0*x0 + x1*x1) with every operation rounded
+// on its own (no FMA contraction; measured on the B200: tools/norm_check.py, 0 of 2^20 values differ).  The same sequence
+// here makes the statistic -- and with it the multinomial densification draws of _uv_densify -- bit-identical to
+// upstream's for the same gradient.
+__device__ __forceinline__ float norm2_like_torch(float gx, float gy) {
+    return __fsqrt_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)));
+}
+
 __global__ void __launch_bounds__(256)
 densify_stats_kernel(int P, const float* __restrict__ grad2d /*[P,3]*/, const uint8_t* __restrict__ filter,
                      float* __restrict__ accum, float* __restrict__ denom) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P || !filter[i]) return;
     const float gx = grad2d[3 * (size_t)i], gy = grad2d[3 * (size_t)i + 1];
-    accum[i] += sqrtf(gx * gx + gy * gy);
+    accum[i] += norm2_like_torch(gx, gy);
     denom[i] += 1.0f;
 }
 // Frame-sharded form: this frame's INCREMENTS written out of place (0 where the splat is not visible), so that they
@@ -26,7 +34,7 @@ densify_stats_inc_kernel(int P, const float* __restrict__ grad2d, const int* __r
     if (i >= P) return;
     const bool vis = radii[i] > 0;
     const float gx = grad2d[3 * (size_t)i], gy = grad2d[3 * (size_t)i + 1];
-    accum_inc[i] = vis ? sqrtf(gx * gx + gy * gy) : 0.0f;
+    accum_inc[i] = vis ? norm2_like_torch(gx, gy) : 0.0f;
     denom_inc[i] = vis ? 1.0f : 0.0f;
 }
 }  // namespace
