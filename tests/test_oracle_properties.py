@@ -36,7 +36,7 @@ def scene_strategy(draw):
     return sc, mode
 
 
-@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+@settings(max_examples=40, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
 @given(scene_strategy())
 def test_forward_invariants(case):
     sc, mode = case
@@ -72,10 +72,18 @@ def test_forward_invariants(case):
     if mode == "behind":
         assert not vis[: max(1, P // 2)].any()
     if mode == "opaque" and (~untouched).any():
-        assert o["final_T"][~untouched].min() < 0.02        # one saturated splat leaves T = 0.01
+        # a splat that saturates (alpha clamps to 0.99) at the pixel nearest to its mean leaves T <= 0.01 there, whatever
+        # lies in front of or behind it (T only shrinks; the 1e-4 stop keeps a T that is already below 0.01)
+        m2, co = o["means2D"][vis].astype(np.float64), o["conic_opacity"][vis].astype(np.float64)
+        px, py = np.rint(m2[:, 0]), np.rint(m2[:, 1])
+        dx, dy = m2[:, 0] - px, m2[:, 1] - py
+        power = -0.5 * (co[:, 0] * dx * dx + co[:, 2] * dy * dy) - co[:, 1] * dx * dy
+        sat = (px >= 0) & (px < W) & (py >= 0) & (py < H) & (power <= 0) & (co[:, 3] * np.exp(power) >= 0.995)
+        for x, y in zip(px[sat].astype(int), py[sat].astype(int)):
+            assert o["final_T"][y, x] < 0.02
 
 
-@settings(max_examples=15, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+@settings(max_examples=15, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
 @given(scene_strategy())
 def test_backward_is_finite_linear_and_silent_where_nothing_was_drawn(case):
     sc, mode = case
